@@ -1,0 +1,214 @@
+"""Generate tests/golden/*.npz by running the REAL reference (/root/reference, imported
+read-only through oracle/ref_shim.py) on seeded synthetic inputs.  TEST INFRASTRUCTURE ONLY.
+
+Run in the build container (the GPU box has no /root/reference):
+
+    python -m oracle.make_golden            # writes tests/golden/*.npz
+
+The reference ships no golden vectors for this path, so these files
+are what pins oracle/chore_oracle.py (tests/test_oracle.py) and, through it, the CUDA path.
+Large inputs (weights, feature maps, SMPL-H-shaped buffers) are not stored: they are
+re-generated from the recorded seeds by the same torch CPU generator calls used here
+(`oracle.chore_oracle.make_state_dict`, `make_smplh_buffers`, `synth_*` below), and a checksum
+of each regenerated input is stored so a generator drift is detected rather than silently
+compared against.
+
+Reference entry points exercised (paths relative to /root/reference):
+  model/chore.py:87-96,107-167   CHORE.filter / CHORE.query / get_preds
+  model/HGFilters.py:144-185     HGFilter.forward
+  recon/generator.py:50-79       Generator.approx_surface
+  lib_smpl/smplpytorch/smplpytorch/pytorch/smpl_layer.py:72-175   SMPL_Layer.forward
+  recon/recon_fit_base.py:167-188,367-384   project_so3 / transform_obj_verts / decopose_axis
+  recon/recon_fit_behave.py:165-222          forward_step(phase='object only')
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+from . import chore_oracle as O
+from . import ref_shim
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+# ------------------------------------------------------------------------------------------
+# seeded synthetic inputs (shared with tests / bench through oracle.chore_oracle re-exports)
+# ------------------------------------------------------------------------------------------
+def checksum(t: torch.Tensor) -> np.ndarray:
+    t = t.detach().double().reshape(-1)
+    idx = torch.arange(t.numel(), dtype=torch.float64)
+    return np.array([t.sum().item(), (t * torch.cos(idx)).sum().item(), t.abs().max().item()])
+
+
+def save(name, **arrays):
+    os.makedirs(OUT, exist_ok=True)
+    conv = {}
+    for k, v in arrays.items():
+        if isinstance(v, torch.Tensor):
+            v = v.detach().cpu().numpy()
+        conv[k] = np.asarray(v)
+    path = os.path.join(OUT, name)
+    np.savez_compressed(path, **conv)
+    print(f"wrote {path}: {os.path.getsize(path) / 1e3:.1f} kB")
+
+
+def gold_query(net):
+    """CHORE.query fwd + gradient to the points on synthetic feature maps, B=2."""
+    seed = 11
+    sd = O.make_state_dict(0, "unit")
+    net.load_state_dict(sd)
+    feat, tmpx = O.synth_features(seed, B=2)
+    pts = torch.cat([O.synth_points("init_box", seed, 2, 1024), O.synth_points("frustum", seed + 1, 2, 1024)], 1)
+    # a few hand-made edge cases: exactly on the image border, behind/at the camera plane, far outside
+    cc = torch.tensor([[1008., 995.], [900., 1100.]])
+    edge = torch.tensor([[0.0, 0.0, 2.2], [5.0, 0.0, 2.2], [0.0, -4.0, 2.2], [0.3, 0.2, 1e-3],
+                         [0.1, 0.1, -1.0], [-0.0102, 0.5288, 2.2], [1e3, 1e3, 2.2], [0.6, -0.4, 2.0]])
+    pts[:, :8] = edge
+    net.im_feat_list, net.tmpx = [feat], tmpx
+    p = pts.clone().requires_grad_(True)
+    net.query(p, crop_center=cc)
+    df, pca, parts, centers = net.get_preds()
+    g = torch.Generator().manual_seed(seed + 2)
+    gd = {k: torch.randn(v.shape, generator=g) for k, v in
+          (("df", df), ("pca", pca), ("parts", parts), ("centers", centers))}
+    (gd["df"] * df).sum().add((gd["pca"] * pca).sum()).add((gd["parts"] * parts).sum()).add(
+        (gd["centers"] * centers).sum()).backward()
+    grad_all = p.grad.clone()
+    # the approx_surface pattern: clamp(df_h, max=2).sum().backward()
+    p2 = pts.clone().requires_grad_(True)
+    net.query(p2, crop_center=cc)
+    torch.clamp(net.get_preds()[0][:, 0, :], max=2.0).sum().backward()
+    xyz = net.camera.project_points(pts, cc) if hasattr(net, "camera") else O.project_points(pts, cc)
+    save("query.npz", seed=seed, weights_seed=0, points=pts, crop_center=cc, df=df, pca=pca, parts=parts,
+         centers=centers, g_df=gd["df"], g_pca=gd["pca"], g_parts=gd["parts"], g_centers=gd["centers"],
+         grad_all=grad_all, grad_dfh=p2.grad, proj=O.project_points(pts, cc),
+         feat_ck=checksum(feat), tmpx_ck=checksum(tmpx), w_ck=checksum(sd["df.0.weight"]))
+
+
+def gold_encoder(net):
+    """HGFilter through CHORE.filter: a 2x5x128x128 batch stored in full, and the 1x5x512x512
+    production shape stored on a stride-8 pixel lattice."""
+    sd = O.make_state_dict(0, "unit")
+    net.load_state_dict(sd)
+    img = O.synth_images(21, B=2, size=128)
+    with torch.no_grad():
+        net.filter(img)
+        feat, tmpx, normx = net.im_feat_list[-1].clone(), net.tmpx.clone(), net.normx.clone()
+    save("encoder_128.npz", seed=21, weights_seed=0, feat=feat, tmpx=tmpx, normx=normx[:, :, ::4, ::4],
+         img_ck=checksum(img))
+    img = O.synth_images(22, B=1, size=512)
+    with torch.no_grad():
+        net.filter(img)
+        feat, tmpx = net.im_feat_list[-1], net.tmpx
+    save("encoder_512.npz", seed=22, weights_seed=0, feat_s8=feat[:, :, ::8, ::8], tmpx_s8=tmpx[:, :, ::8, ::8],
+         feat_ck=checksum(feat), tmpx_ck=checksum(tmpx), img_ck=checksum(img))
+    # reference-faithful init (N(0, 0.02), zero bias): magnitudes only, as a second weight family
+    sd2 = O.make_state_dict(1, "ref_init")
+    net.load_state_dict(sd2)
+    img = O.synth_images(23, B=1, size=128)
+    with torch.no_grad():
+        net.filter(img)
+    save("encoder_128_refinit.npz", seed=23, weights_seed=1, feat=net.im_feat_list[-1], tmpx=net.tmpx)
+
+
+def gold_approx_surface(net):
+    """Generator.approx_surface, 10 steps, both distance fields (recon/generator.py:50-79)."""
+    Generator = ref_shim.load_generator_class()
+    sd = O.make_state_dict(0, "unit")
+    net.load_state_dict(sd)
+    feat, tmpx = O.synth_features(31, B=1)
+    net.im_feat_list, net.tmpx = [feat], tmpx
+    cc = torch.tensor([[1008., 995.]])
+    fake = types.SimpleNamespace(threshold=2.0)
+    out = {}
+    for name in ("human", "object"):
+        s = O.synth_points("frustum", 32, 1, 512).requires_grad_(True)
+        samples, preds = Generator.approx_surface(fake, net, s, 10, {"crop_center": cc}, name)
+        out[f"samples_{name}"] = samples.detach()
+        out[f"df_{name}"] = preds[0].detach()
+    save("approx_surface.npz", seed=31, weights_seed=0, crop_center=cc, **out)
+
+
+def gold_lbs():
+    """SMPL_Layer.forward on synthetic SMPL-H-shaped buffers + gradients to pose/betas/trans."""
+    buf = O.make_smplh_buffers(0)
+    layer = ref_shim.load_smpl_layer(buf)
+    g = torch.Generator().manual_seed(41)
+    B = 2
+    pose = (0.2 * torch.randn(B, 156, generator=g)).requires_grad_(True)
+    pose.data[1, 6:9] = 0.0                       # an exactly-zero joint rotation (the 1e-8 branch)
+    betas = torch.randn(B, 10, generator=g).requires_grad_(True)
+    trans = (torch.tensor([[0.0, 0.0, 2.2]]) + 0.1 * torch.randn(B, 3, generator=g)).requires_grad_(True)
+    offsets = (0.003 * torch.randn(B, 6890, 3, generator=g)).requires_grad_(True)
+    verts, jtr, v_posed, naked = layer(pose, th_betas=betas, th_trans=trans, th_offsets=offsets)
+    g_verts = torch.randn(verts.shape, generator=g)
+    g_jtr = torch.randn(jtr.shape, generator=g)
+    ((g_verts * verts).sum() + (g_jtr * jtr).sum()).backward()
+    save("lbs.npz", seed=41, buffers_seed=0, pose=pose, betas=betas, trans=trans, offsets=offsets,
+         verts=verts, jtr=jtr, v_posed_s=v_posed[:, ::10], naked_s=naked[:, ::10],
+         g_verts=g_verts, g_jtr=g_jtr, grad_pose=pose.grad, grad_betas=betas.grad, grad_trans=trans.grad,
+         grad_offsets_s=offsets.grad[:, ::10], posedirs_ck=checksum(buf["posedirs"]),
+         weights_ck=checksum(buf["weights"]))
+
+
+def gold_rigid_and_fit(net):
+    """transform_obj_verts / project_so3 / decopose_axis and one 'object only' forward_step with
+    backward to (R, t, s) (recon/recon_fit_behave.py:165-198)."""
+    Fitter = ref_shim.load_fitter_class()
+    fit = object.__new__(Fitter)
+    fit.debug = False
+    fit.obj_scale = 1.0
+    g = torch.Generator().manual_seed(51)
+    B, No = 2, 3000
+    obj = 0.2 * torch.randn(B, No, 3, generator=g)
+    rot = (torch.eye(3).unsqueeze(0) + 0.2 * torch.randn(B, 3, 3, generator=g)).requires_grad_(True)
+    t = (torch.tensor([[0.2, 0.1, 2.3]]) + 0.05 * torch.randn(B, 3, generator=g)).requires_grad_(True)
+    s = (1.0 + 0.05 * torch.randn(B, generator=g)).requires_grad_(True)
+    R0 = Fitter.project_so3(rot.detach())
+    moved = fit.transform_obj_verts(obj, R0, t.detach(), s.detach())
+    bad = torch.eye(3).unsqueeze(0).repeat(2, 1, 1)
+    bad[1, 2, 2] = -1.0                            # det < 0 input
+    save("rigid.npz", seed=51, obj=obj, rot=rot, t=t, s=s, R=R0, moved=moved, bad=bad, R_bad=Fitter.project_so3(bad))
+
+    sd = O.make_state_dict(0, "unit")
+    net.load_state_dict(sd)
+    feat, tmpx = O.synth_features(52, B=B)
+    net.im_feat_list, net.tmpx = [feat], tmpx
+    cc = torch.tensor([[1008., 995.], [1000., 980.]])
+    smpl_center = torch.tensor([[0.0, 0.1, 2.2], [0.05, 0.0, 2.25]])
+    data = {"objects": obj, "query_dict": {"crop_center": cc}, "smpl_center": smpl_center}
+    torch.manual_seed(53)
+    noise = torch.rand(B, 3, 3)                    # what decopose_axis will draw (recon_fit_base.py:384)
+    torch.manual_seed(53)
+    smpl = lambda: (torch.zeros(B, 6890, 3), None, None, None)
+    losses = fit.forward_step(net, smpl, data, rot, t, s, "object only")
+    import recon.recon_fit_behave  # noqa: F401  (already imported by load_fitter_class)
+    wts = fit.get_loss_weights()
+    total = fit.sum_dict(losses, wts, 3)
+    total.backward()
+    save("fit_object_only.npz", seed=52, weights_seed=0, obj=obj, rot=rot, t=t, s=s, crop_center=cc,
+         smpl_center=smpl_center, noise=noise, it=3, loss_object=losses["object"], loss_scale=losses["scale"],
+         loss_ocent=losses["ocent"], total=total, grad_rot=rot.grad, grad_t=t.grad, grad_s=s.grad)
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    if not ref_shim.available():
+        sys.exit("reference tree not available: goldens can only be generated in the build container")
+    net, _ = ref_shim.load_chore()
+    with ref_shim.ref_cwd():
+        gold_query(net)
+        gold_encoder(net)
+        gold_approx_surface(net)
+        gold_lbs()
+        gold_rigid_and_fit(net)
+
+
+if __name__ == "__main__":
+    main()

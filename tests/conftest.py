@@ -1,0 +1,43 @@
+"""pytest configuration: `gpu` marker (needs a real B200 + the built libchore_b200.so) and
+shared helpers.  `-m "not gpu"` must pass on a CPU-only box."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def pytest_collection_modifyitems(config, items):
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:  # pragma: no cover
+        has_gpu = False
+    if has_gpu:
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN, name)))
+
+
+def rel_err(a, b):
+    """max |a-b| / (|b| + rms(b)): the relative-error measure used for the 1e-4 field bar."""
+    import torch
+    a = torch.as_tensor(a).double().cpu()
+    b = torch.as_tensor(b).double().cpu()
+    scale = b.abs() + b.pow(2).mean().sqrt() + 1e-30
+    return ((a - b).abs() / scale).max().item()
