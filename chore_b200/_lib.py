@@ -1,0 +1,276 @@
+"""ctypes binding of libchore_b200.so (include/chore_b200.h).
+
+The product path has no CPU or eager fallback: if the library is missing or the device is not
+sm_100 every entry point raises.  torch is used only for device memory and streams
+(`tensor.data_ptr()`, `torch.cuda.current_stream()`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Dict, Iterable, Optional, Tuple
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libchore_b200.so")
+
+HEAD_DF, HEAD_PCA, HEAD_PARTS, HEAD_CENTERS, HEAD_ALL = 1, 2, 4, 8, 15
+HEAD_OUT = (2, 9, 14, 6)   # kernel head order: df, pca, parts, centers
+
+
+class ChoreError(RuntimeError):
+    pass
+
+
+class TensorDesc(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("ndim", C.c_int), ("shape", C.c_int64 * 4),
+                ("on_device", C.c_int)]
+
+
+_P, _I, _U32, _I64 = C.c_void_p, C.c_int, C.c_uint32, C.c_int64
+# every symbol include/chore_b200.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "chore_create": (_I, [_I, C.POINTER(_P)]),
+    "chore_destroy": (None, [_P]),
+    "chore_last_error": (C.c_char_p, []),
+    "chore_abi_version": (_I, []),
+    "chore_launch_count": (C.c_uint64, []),
+    "chore_load_weights": (_I, [_P, C.POINTER(TensorDesc), _I]),
+    "chore_encode": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "chore_query_fwd": (_I, [_P, _P, _P, _I, _I, _P, _P, _I, _I, _U32, _P, _P, _P, _P, _P, _P]),
+    "chore_query_bwd": (_I, [_P, _P, _P, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "chore_query_grid": (_I, [_P, _P, _P, _I, _I, _P, _I, C.POINTER(_I), C.POINTER(C.c_float), C.POINTER(C.c_float),
+                              _I64, _I64, _U32, _P, _P, _P, _P, _P]),
+    "chore_lbs_load_model": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I]),
+    "chore_lbs_fwd": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P]),
+    "chore_lbs_bwd": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "chore_rigid_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P]),
+    "chore_rigid_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "chore_project_so3": (_I, [_P, _P, _I, _P, _P]),
+    "chore_project_so3_bwd": (_I, [_P, _P, _P, _I, _P, _P]),
+}
+
+_lib = None
+_lock = threading.RLock()
+_handles: Dict[int, "Handle"] = {}
+
+
+def load_library() -> C.CDLL:
+    """dlopen the in-tree library and type every entry point.  Raises if it is not built."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise ChoreError(f"{LIB_PATH} is missing: build it with `python -m chore_b200.build` "
+                             "(there is no CPU / PyTorch fallback for the CHORE hot path)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)     # AttributeError here = header / library mismatch
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+        return lib
+
+
+def launch_count() -> int:
+    return int(load_library().chore_launch_count())
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def check_cuda(*tensors: Optional[torch.Tensor]) -> None:
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise ChoreError(f"expected a contiguous fp32 CUDA tensor, got {t.dtype} {t.device} "
+                             f"contiguous={t.is_contiguous()} shape={tuple(t.shape)}")
+
+
+class Handle:
+    """One chore_handle per CUDA device."""
+
+    def __init__(self, device: int):
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise ChoreError("no CUDA device: the CHORE hot path runs on sm_100a only (no CPU fallback)")
+        self.device = device
+        h = _P()
+        self._check(self.lib.chore_create(device, C.byref(h)))
+        self.h = h
+        self._keep = []          # host tensors that must outlive a call
+
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            raise ChoreError(f"libchore_b200 error {rc}: {self.lib.chore_last_error().decode()}")
+
+    def close(self) -> None:
+        if self.h:
+            self.lib.chore_destroy(self.h)
+            self.h = None
+
+    # ---- weights -------------------------------------------------------------------------
+    def load_weights(self, state_dict: Dict[str, torch.Tensor]) -> None:
+        items = [(k, v.detach().float().contiguous()) for k, v in state_dict.items() if torch.is_tensor(v) and v.dim() >= 1]
+        arr = (TensorDesc * len(items))()
+        for d, (k, v) in zip(arr, items):
+            d.name = k.encode()
+            d.data = v.data_ptr()
+            d.ndim = min(v.dim(), 4) if v.dim() != 3 else 3
+            for i, s in enumerate(v.shape[:4]):
+                d.shape[i] = s
+            d.on_device = int(v.is_cuda)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.chore_load_weights(self.h, arr, len(items)))
+
+    # ---- encoder -------------------------------------------------------------------------
+    def encode(self, images: torch.Tensor, want_normx: bool = True) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+        check_cuda(images)
+        B, Cin, H, W = images.shape
+        if Cin != 5:
+            raise ChoreError(f"images must have 5 channels (RGB + 2 masks), got {Cin}")
+        feat = torch.empty(B, H // 4, W // 4, 256, device=images.device)
+        skip = torch.empty(B, H // 2, W // 2, 64, device=images.device)
+        normx = torch.empty(B, H // 4, W // 4, 128, device=images.device) if want_normx else None
+        with torch.cuda.device(self.device):
+            self._check(self.lib.chore_encode(self.h, images.data_ptr(), B, H, W, feat.data_ptr(), skip.data_ptr(),
+                                              _ptr(normx), _stream()))
+        return feat, skip, normx
+
+    # ---- point query ---------------------------------------------------------------------
+    def query_fwd(self, feat: torch.Tensor, skip: torch.Tensor, points: torch.Tensor, crop_center: torch.Tensor,
+                  head_mask: int = HEAD_ALL, want_in_img: bool = False):
+        check_cuda(feat, skip, points, crop_center)
+        B, N = points.shape[0], points.shape[1]
+        fh, fw = feat.shape[1], feat.shape[2]
+        if feat.shape[0] != B or feat.shape[3] != 256 or tuple(skip.shape) != (B, 2 * fh, 2 * fw, 64):
+            raise ChoreError(f"feature maps {tuple(feat.shape)} / {tuple(skip.shape)} do not match B={B}")
+        if tuple(crop_center.shape) != (B, 2) or points.shape[2] != 3:
+            raise ChoreError("points must be (B,N,3) and crop_center (B,2)")
+        outs = [torch.empty(B, c, N, device=points.device) if head_mask & (1 << i) else None
+                for i, c in enumerate(HEAD_OUT)]
+        in_img = torch.empty(B, N, dtype=torch.uint8, device=points.device) if want_in_img else None
+        if N == 0:                      # empty query: nothing to launch (data_ptr() of an empty tensor is NULL)
+            return outs, in_img
+        with torch.cuda.device(self.device):
+            self._check(self.lib.chore_query_fwd(self.h, feat.data_ptr(), skip.data_ptr(), fh, fw, points.data_ptr(),
+                                                 crop_center.data_ptr(), B, N, head_mask, *[_ptr(o) for o in outs],
+                                                 _ptr(in_img), _stream()))
+        return outs, in_img
+
+    def query_bwd(self, feat, skip, points, crop_center, grads: Iterable[Optional[torch.Tensor]]) -> torch.Tensor:
+        grads = [None if g is None else g.contiguous() for g in grads]
+        check_cuda(feat, skip, points, crop_center, *grads)
+        B, N = points.shape[0], points.shape[1]
+        g_points = torch.empty_like(points)
+        if N == 0:
+            return g_points
+        with torch.cuda.device(self.device):
+            self._check(self.lib.chore_query_bwd(self.h, feat.data_ptr(), skip.data_ptr(), feat.shape[1], feat.shape[2],
+                                                 points.data_ptr(), crop_center.data_ptr(), B, N,
+                                                 *[_ptr(g) for g in grads], g_points.data_ptr(), _stream()))
+        return g_points
+
+    def query_grid(self, feat, skip, crop_center, b: int, res, b_min, b_max, start: int, count: int,
+                   head_mask: int, outs) -> None:
+        """outs: per-head (nout, total) tensors of image b (or None); fills columns [start, start+count)."""
+        check_cuda(feat, skip, crop_center, *outs)
+        res_c = (_I * 3)(*[int(r) for r in res])
+        mn = (C.c_float * 3)(*[float(x) for x in b_min])
+        mx = (C.c_float * 3)(*[float(x) for x in b_max])
+        with torch.cuda.device(self.device):
+            self._check(self.lib.chore_query_grid(self.h, feat.data_ptr(), skip.data_ptr(), feat.shape[1], feat.shape[2],
+                                                  crop_center.data_ptr(), b, res_c, mn, mx, start, count, head_mask,
+                                                  *[_ptr(o) for o in outs], _stream()))
+
+    # ---- SMPL-H ----------------------------------------------------------------------------
+    def lbs_load_model(self, v_template, shapedirs, posedirs, J_regressor, weights, parents) -> None:
+        ts = [t.detach().float().contiguous().cpu() for t in (v_template, shapedirs, posedirs, J_regressor, weights)]
+        par = torch.as_tensor(parents).to(torch.int32).contiguous().cpu()
+        V, J, nb = ts[4].shape[0], ts[4].shape[1], ts[1].shape[-1]
+        with torch.cuda.device(self.device):
+            self._check(self.lib.chore_lbs_load_model(self.h, *[t.data_ptr() for t in ts], par.data_ptr(), V, J, nb, 0))
+        self.lbs_shape = (V, J, nb)
+
+    def lbs_fwd(self, pose, betas, trans, offsets, want_posed: bool = True):
+        check_cuda(pose, betas, trans, offsets)
+        V, J, _ = self.lbs_shape
+        B = pose.shape[0]
+        verts = torch.empty(B, V, 3, device=pose.device)
+        jtr = torch.empty(B, J, 3, device=pose.device)
+        v_posed = torch.empty(B, V, 3, device=pose.device) if want_posed else None
+        naked = torch.empty(B, V, 3, device=pose.device) if want_posed else None
+        with torch.cuda.device(self.device):
+            self._check(self.lib.chore_lbs_fwd(self.h, pose.data_ptr(), betas.data_ptr(), trans.data_ptr(), _ptr(offsets),
+                                               B, verts.data_ptr(), jtr.data_ptr(), _ptr(v_posed), _ptr(naked), _stream()))
+        return verts, jtr, v_posed, naked
+
+    def lbs_bwd(self, pose, betas, trans, offsets, g_verts, g_jtr, want_offsets: bool):
+        g_verts = g_verts.contiguous()
+        g_jtr = None if g_jtr is None else g_jtr.contiguous()
+        check_cuda(pose, betas, trans, offsets, g_verts, g_jtr)
+        B = pose.shape[0]
+        g_pose, g_betas, g_trans = torch.empty_like(pose), torch.empty_like(betas), torch.empty_like(trans)
+        g_off = torch.empty_like(g_verts) if want_offsets else None
+        with torch.cuda.device(self.device):
+            self._check(self.lib.chore_lbs_bwd(self.h, pose.data_ptr(), betas.data_ptr(), trans.data_ptr(), _ptr(offsets),
+                                               B, g_verts.data_ptr(), _ptr(g_jtr), g_pose.data_ptr(), g_betas.data_ptr(),
+                                               g_trans.data_ptr(), _ptr(g_off), _stream()))
+        return g_pose, g_betas, g_trans, g_off
+
+    # ---- rigid object ------------------------------------------------------------------------
+    def rigid_fwd(self, verts, R, t, s):
+        check_cuda(verts, R, t, s)
+        out = torch.empty_like(verts)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.chore_rigid_fwd(self.h, verts.data_ptr(), R.data_ptr(), t.data_ptr(), s.data_ptr(),
+                                                 verts.shape[0], verts.shape[1], out.data_ptr(), _stream()))
+        return out
+
+    def rigid_bwd(self, verts, R, t, s, g_out, want_verts: bool):
+        g_out = g_out.contiguous()
+        check_cuda(verts, R, t, s, g_out)
+        g_R, g_t, g_s = torch.empty_like(R), torch.empty_like(t), torch.empty_like(s)
+        g_v = torch.empty_like(verts) if want_verts else None
+        with torch.cuda.device(self.device):
+            self._check(self.lib.chore_rigid_bwd(self.h, verts.data_ptr(), R.data_ptr(), t.data_ptr(), s.data_ptr(),
+                                                 verts.shape[0], verts.shape[1], g_out.data_ptr(), g_R.data_ptr(),
+                                                 g_t.data_ptr(), g_s.data_ptr(), _ptr(g_v), _stream()))
+        return g_R, g_t, g_s, g_v
+
+    def project_so3(self, mats):
+        check_cuda(mats)
+        out = torch.empty_like(mats)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.chore_project_so3(self.h, mats.data_ptr(), mats.shape[0], out.data_ptr(), _stream()))
+        return out
+
+    def project_so3_bwd(self, mats, g_out):
+        g_out = g_out.contiguous()
+        check_cuda(mats, g_out)
+        g = torch.empty_like(mats)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.chore_project_so3_bwd(self.h, mats.data_ptr(), g_out.data_ptr(), mats.shape[0],
+                                                       g.data_ptr(), _stream()))
+        return g
+
+
+def get_handle(device=None) -> Handle:
+    """The process-wide handle of a CUDA device (created on first use)."""
+    load_library()
+    if not torch.cuda.is_available():
+        raise ChoreError("no CUDA device: the CHORE hot path runs on sm_100a only (no CPU fallback)")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    with _lock:
+        if idx not in _handles:
+            _handles[idx] = Handle(idx)
+        return _handles[idx]

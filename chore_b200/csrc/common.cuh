@@ -1,0 +1,134 @@
+// Shared declarations of libchore_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/chore_b200.h"
+
+// ---- error plumbing ---------------------------------------------------------------------
+void chore_set_error(const char *fmt, ...);
+extern std::atomic<uint64_t> g_launch_count;
+
+#define CHORE_CUDA(call)                                                                     \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess) {                                                             \
+            chore_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return CHORE_ERR_CUDA;                                                           \
+        }                                                                                    \
+    } while (0)
+
+#define CHORE_CHECK(cond, ...)                                                               \
+    do {                                                                                     \
+        if (!(cond)) {                                                                       \
+            chore_set_error(__VA_ARGS__);                                                    \
+            return CHORE_ERR_INVALID;                                                        \
+        }                                                                                    \
+    } while (0)
+
+// every kernel launch goes through this so chore_launch_count() is exact
+#define CHORE_LAUNCH(kernel, grid, block, smem, stream, ...)                                 \
+    do {                                                                                     \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                          \
+        g_launch_count.fetch_add(1, std::memory_order_relaxed);                              \
+        CHORE_CUDA(cudaGetLastError());                                                      \
+    } while (0)
+
+// ---- constants of the chore-release configuration ------------------------------------------
+constexpr int kFeatC = CHORE_FEAT_CH;     // 256
+constexpr int kSkipC = CHORE_SKIP_CH;     // 64
+constexpr int kPointC = CHORE_POINT_CH;   // 323
+constexpr int kPointCPad = 324;           // padded to a multiple of 4
+constexpr int kHidden = 128;
+constexpr int kNumHeads = 4;              // kernel order: df, pca, parts, centers
+constexpr int kHeadOut[kNumHeads] = {2, 9, 14, 6};
+constexpr int kW1oLd = 384;               // leading dimension of the [512][323] layout (3 x 128)
+
+// ---- MLP weights in kernel layouts ------------------------------------------------------------
+struct MlpWeights {
+    // "t" layouts are [K][N] (input-major), used by the forward GEMMs;
+    // "o" layouts are the PyTorch [out][in] layouts, used as [K][N] by the backward GEMMs.
+    float *w1t = nullptr;   // [324][512]   heads concatenated along N (head h at cols 128h)
+    float *w1o = nullptr;   // [512][384]   zero padded beyond col 323
+    float *b1 = nullptr;    // [512]
+    float *w2t = nullptr, *w2o = nullptr, *b2 = nullptr;   // [4][128][128], [4][128]
+    float *w3t = nullptr, *w3o = nullptr, *b3 = nullptr;
+    float *w4 = nullptr;    // [4][16][128]  rows >= n_out zero
+    float *b4 = nullptr;    // [4][16]
+    bool loaded = false;
+};
+
+// ---- encoder weights ------------------------------------------------------------------------------
+struct ConvW {
+    float *w = nullptr;     // [kh][kw][cin][cout]  (HWIO)
+    float *bias = nullptr;  // [cout] or null
+    int kh = 0, kw = 0, cin = 0, cout = 0;
+};
+struct NormW {
+    float *gamma = nullptr, *beta = nullptr;
+    int c = 0;
+};
+struct EncoderWeights {
+    std::map<std::string, ConvW> conv;
+    std::map<std::string, NormW> norm;
+    bool loaded = false;
+};
+
+// ---- SMPL-H body model ----------------------------------------------------------------------------
+struct LbsModel {
+    int V = 0, J = 0, nb = 0;
+    float *v_template = nullptr;   // [V][3]
+    float *shapedirs = nullptr;    // [V][3][nb]
+    float *posedirs = nullptr;     // [V][3][(J-1)*9]
+    float *weights = nullptr;      // [V][J]
+    float *j_template = nullptr;   // [J][3]      = J_regressor . v_template
+    float *j_shapedirs = nullptr;  // [J][3][nb]  = J_regressor . shapedirs
+    int32_t *parents = nullptr;    // device [J]
+    std::vector<int> parents_h;
+    bool loaded = false;
+};
+
+struct chore_handle {
+    int device = 0;
+    int sm_count = 148;
+    MlpWeights mlp;
+    EncoderWeights enc;
+    LbsModel lbs;
+    // growable scratch (encoder activations, LBS intermediates)
+    void *ws = nullptr;
+    size_t ws_bytes = 0;
+    void *ws2 = nullptr;
+    size_t ws2_bytes = 0;
+    void *lbs_ws = nullptr;      // LBS / rigid intermediates (own buffer: may interleave with encode)
+    size_t lbs_ws_bytes = 0;
+    std::vector<void *> owned;   // device allocations released by chore_destroy
+};
+
+int chore_ws_reserve(chore_handle *h, size_t bytes);    // (re)allocates h->ws
+int chore_ws2_reserve(chore_handle *h, size_t bytes);   // (re)allocates h->ws2
+int chore_lbs_ws_reserve(chore_handle *h, size_t bytes);
+int chore_dev_alloc(chore_handle *h, void **p, size_t bytes);
+
+// implemented per translation unit
+int query_load_weights(chore_handle *h, const std::map<std::string, const chore_tensor_desc *> &t);
+int encoder_load_weights(chore_handle *h, const std::map<std::string, const chore_tensor_desc *> &t);
+
+// ---- small device helpers ------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}

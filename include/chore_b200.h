@@ -1,0 +1,157 @@
+/* chore_b200.h -- C ABI of libchore_b200.so, the sm_100a implementation of the CHORE hot path.
+ *
+ * The reference (xiexh20/CHORE) has no FFI: its hot path is Python duck-typing on
+ * BasePIFuNet.filter/query/get_preds, the SMPL wrapper's forward() and three ReconFitterBase
+ * helpers.  This header is the boundary a maintainer binds instead of the
+ * torch ops listed beside every entry point (paths relative to the reference tree).  The
+ * ctypes binding that the Python host side uses is chore_b200/_lib.py; INTEGRATION.md shows the
+ * reference-side stub.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / C++ types.
+ *   - every data pointer is a DEVICE pointer to fp32 unless the comment says otherwise.
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it.
+ *   - return value: 0 = ok, otherwise a chore_status; chore_last_error() gives the text
+ *     (thread-local).  Nothing throws across the ABI.
+ *   - the caller owns every buffer; the handle owns the repacked weights and its workspace.
+ *   - one handle per device; calls on one handle must not be issued concurrently.
+ */
+#ifndef CHORE_B200_H
+#define CHORE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct chore_handle chore_handle;
+
+enum chore_status {
+    CHORE_OK = 0,
+    CHORE_ERR_INVALID = 1,      /* bad argument (null pointer, bad shape)          */
+    CHORE_ERR_CUDA = 2,         /* a CUDA runtime call failed                       */
+    CHORE_ERR_NO_WEIGHTS = 3,   /* weights / body model not loaded yet              */
+    CHORE_ERR_ARCH = 4          /* device is not sm_100                             */
+};
+
+/* constants of config/chore-release.json that the kernels are compiled for */
+#define CHORE_IN_CH 5        /* RGBM3 input: RGB + person mask + object mask         */
+#define CHORE_FEAT_CH 256    /* hourglass_dim                                        */
+#define CHORE_SKIP_CH 64     /* stem width (tmpx skip feature)                       */
+#define CHORE_POINT_CH 323   /* 256 + (x, y, z-2.2) + 64  (model/chore.py:139-143)   */
+#define CHORE_NUM_PARTS 14
+#define CHORE_SMPLH_VERTS 6890
+#define CHORE_SMPLH_JOINTS 52
+
+/* head_mask bits for chore_query_fwd / chore_query_bwd */
+#define CHORE_HEAD_DF 1u
+#define CHORE_HEAD_PCA 2u
+#define CHORE_HEAD_PARTS 4u
+#define CHORE_HEAD_CENTERS 8u
+#define CHORE_HEAD_ALL 15u
+
+/* one named fp32 tensor of the reference state_dict (checkpoint['model_state_dict'],
+ * recon/generator.py:243-267; an optional "module." prefix is accepted) */
+typedef struct {
+    const char *name;      /* e.g. "image_filter.conv1.weight", "df.0.weight"        */
+    const float *data;     /* contiguous fp32, PyTorch layout                        */
+    int ndim;
+    int64_t shape[4];
+    int on_device;         /* 0: host pointer, 1: device pointer                     */
+} chore_tensor_desc;
+
+/* ---- lifetime ---------------------------------------------------------------------- */
+int chore_create(int device, chore_handle **out);
+void chore_destroy(chore_handle *h);
+const char *chore_last_error(void);
+/* ABI version and the number of kernels launched through this library since load
+ * (bench.py reports the latter as gpu_launches). */
+int chore_abi_version(void);
+uint64_t chore_launch_count(void);
+
+/* ---- weights: replaces nn.Module.load_state_dict (recon/generator.py:264) ------------- */
+/* Repacks the reference tensors into the kernel layouts.  Tensors it does not know are
+ * ignored; missing ones make the later calls fail with CHORE_ERR_NO_WEIGHTS. */
+int chore_load_weights(chore_handle *h, const chore_tensor_desc *tensors, int n);
+
+/* ---- encoder: replaces HGFilter.forward (model/HGFilters.py:144-185) called from
+ *      CHORE.filter (model/chore.py:87-96), eval mode (last stack output only) -------- */
+/* images: (B,5,H,W) NCHW in [0,1], H and W multiples of 16.
+ * feat:   (B,H/4,W/4,256) NHWC  = im_feat_list[-1] of the reference, channels-last.
+ * skip:   (B,H/2,W/2,64)  NHWC  = tmpx (post-ReLU stem), channels-last.
+ * normx:  (B,H/4,W/4,128) NHWC or NULL. */
+int chore_encode(chore_handle *h, const float *images, int B, int H, int W,
+                 float *feat, float *skip, float *normx, void *stream);
+
+/* ---- point query: replaces CHORE.query + decode (model/chore.py:107-167), i.e.
+ *      KinectColorCamera.project_points (model/camera.py:44-88), index() twice
+ *      (model/geometry.py:4-14), torch.cat, 16 conv1d, and the OUT_DIST masked write ---- */
+/* feat (B,fh,fw,256) NHWC, skip (B,2fh,2fw,64) NHWC, points (B,N,3), crop_center (B,2).
+ * Outputs in the reference layout: df (B,2,N), pca (B,9,N) (viewed (B,3,3,N) by the
+ * caller), parts (B,14,N), centers (B,6,N); any output of a head not in head_mask may be
+ * NULL.  in_img: (B,N) uint8 or NULL. */
+int chore_query_fwd(chore_handle *h, const float *feat, const float *skip, int fh, int fw,
+                    const float *points, const float *crop_center, int B, int N,
+                    uint32_t head_mask, float *df, float *pca, float *parts, float *centers,
+                    uint8_t *in_img, void *stream);
+
+/* gradient of sum_k <g_k, head_k> w.r.t. the points: what the reference's callers get from
+ * loss.backward() through conv1d/grid_sampler/projection (recon/generator.py:63-70,
+ * recon/recon_fit_behave.py:149-152).  g_* have the forward output layouts; NULL = zero.
+ * g_points: (B,N,3), overwritten. */
+int chore_query_bwd(chore_handle *h, const float *feat, const float *skip, int fh, int fw,
+                    const float *points, const float *crop_center, int B, int N,
+                    const float *g_df, const float *g_pca, const float *g_parts,
+                    const float *g_centers, float *g_points, void *stream);
+
+/* dense grid of model/sdf.py:4-48 (create_grid + batch_eval) evaluated without
+ * materialising the coordinates: point i = (ix*ry + iy)*rz + iz (np.mgrid order),
+ * coord = b_min + (b_max-b_min)/res * idx.  Evaluates points [start, start+count). */
+int chore_query_grid(chore_handle *h, const float *feat, const float *skip, int fh, int fw,
+                     const float *crop_center, int b, const int res[3], const float b_min[3],
+                     const float b_max[3], int64_t start, int64_t count, uint32_t head_mask,
+                     float *df, float *pca, float *parts, float *centers, void *stream);
+
+/* ---- SMPL-H linear blend skinning: replaces SMPL_Layer.forward
+ *      (lib_smpl/smplpytorch/smplpytorch/pytorch/smpl_layer.py:72-175) ----------------- */
+/* body-model buffers in the reference's registered-buffer layouts (smpl_layer.py:49-64):
+ * v_template (V,3), shapedirs (V,3,10), posedirs (V,3,(J-1)*9), J_regressor (J,V) dense,
+ * weights (V,J), parents (J) int32 (kintree_table row 0).  Host or device pointers. */
+int chore_lbs_load_model(chore_handle *h, const float *v_template, const float *shapedirs,
+                         const float *posedirs, const float *J_regressor, const float *weights,
+                         const int32_t *parents, int V, int J, int n_betas, int on_device);
+/* pose (B,J*3) axis-angle, betas (B,n_betas), trans (B,3), offsets (B,V,3) or NULL ->
+ * verts (B,V,3), jtr (B,J,3), v_posed (B,V,3) or NULL, naked (B,V,3) or NULL. */
+int chore_lbs_fwd(chore_handle *h, const float *pose, const float *betas, const float *trans,
+                  const float *offsets, int B, float *verts, float *jtr, float *v_posed,
+                  float *naked, void *stream);
+/* analytic backward of the same call (inputs are re-read; nothing is saved by fwd).
+ * g_verts (B,V,3), g_jtr (B,J,3) or NULL -> g_pose (B,J*3), g_betas (B,n_betas),
+ * g_trans (B,3), g_offsets (B,V,3) or NULL. */
+int chore_lbs_bwd(chore_handle *h, const float *pose, const float *betas, const float *trans,
+                  const float *offsets, int B, const float *g_verts, const float *g_jtr,
+                  float *g_pose, float *g_betas, float *g_trans, float *g_offsets, void *stream);
+
+/* ---- rigid object transform: replaces ReconFitterBase.transform_obj_verts
+ *      (recon/recon_fit_base.py:367-371): out = (verts @ R + t) * s --------------------- */
+/* verts (B,N,3), R (B,3,3), t (B,3), s (B) -> out (B,N,3) */
+int chore_rigid_fwd(chore_handle *h, const float *verts, const float *R, const float *t,
+                    const float *s, int B, int N, float *out, void *stream);
+/* g_out (B,N,3) -> g_R (B,3,3), g_t (B,3), g_s (B), g_verts (B,N,3) or NULL */
+int chore_rigid_bwd(chore_handle *h, const float *verts, const float *R, const float *t,
+                    const float *s, int B, int N, const float *g_out, float *g_R, float *g_t,
+                    float *g_s, float *g_verts, void *stream);
+
+/* SO(3) projection R = U diag(1,1,det(U V^T)) V^T: replaces ReconFitterBase.project_so3
+ * (recon/recon_fit_base.py:167-188; torch.svd of a 3x3).  mats, out: (B,3,3). */
+int chore_project_so3(chore_handle *h, const float *mats, int B, float *out, void *stream);
+/* adjoint of the projection (what autograd derives through torch.svd in the reference):
+ * g_out (B,3,3) -> g_mats (B,3,3) */
+int chore_project_so3_bwd(chore_handle *h, const float *mats, const float *g_out, int B,
+                          float *g_mats, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHORE_B200_H */

@@ -1,0 +1,366 @@
+"""GPU parity tests: the CUDA path (through the C ABI via chore_b200) against the oracle and the
+golden vectors generated from the live reference (tests/golden, oracle/make_golden.py).
+
+Bars (BASELINE.json north_star): distance / centre / PCA fields within 1e-4 relative
+(conftest.rel_err: max |a-b| / (|b| + rms(b))); in-image masks and texel indices bit-exact;
+part-label argmax exact wherever the reference's own top-2 logit margin exceeds the fp32
+summation-order noise (the golden vectors contain margins down to 8e-6).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+from oracle import chore_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+DEV = "cuda:0"
+
+
+def T(x, dev=DEV):
+    return torch.from_numpy(np.asarray(x)).to(dev)
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return O.make_state_dict(0, "unit")
+
+
+@pytest.fixture(scope="module")
+def net(sd):
+    import chore_b200
+    n = chore_b200.CHORE(device=DEV)
+    n.load_state_dict(sd)
+    return n.eval()
+
+
+def set_maps(net, feat, tmpx):
+    net.im_feat_list, net.tmpx = [feat.to(DEV)], tmpx.to(DEV)
+
+
+def argmax_agrees(got, ref, margin=5e-4):
+    """argmax must agree wherever the reference's top-2 margin exceeds `margin`."""
+    got, ref = got.cpu(), ref.cpu()
+    top2 = ref.topk(2, dim=1).values
+    clear = (top2[:, 0] - top2[:, 1]) > margin
+    same = got.argmax(1) == ref.argmax(1)
+    assert bool(same[clear].all()), f"{int((~same & clear).sum())} clear-margin labels differ"
+    return int((~same).sum()), int((~clear).sum())
+
+
+def grad_close(got, want, tol=2e-4, frac=0.9995, worst=5e-2):
+    """Gradients to the points: a hidden unit whose pre-activation is within rounding of zero can
+    flip its ReLU mask under a different fp32 summation order, which changes that ONE point's
+    gradient discretely (61 M hidden units are evaluated for 20 k points).  So: all but a
+    vanishing fraction of the points within `tol`, and no point off by more than `worst`."""
+    got, want = got.detach().double().cpu().reshape(-1, 3), want.detach().double().cpu().reshape(-1, 3)
+    scale = want.abs().amax(-1) + want.pow(2).mean().sqrt() + 1e-30
+    err = (got - want).abs().amax(-1) / scale
+    assert (err < tol).double().mean().item() >= frac, ((err < tol).double().mean().item(), err.max().item())
+    assert err.max().item() < worst, err.max().item()
+
+
+# ------------------------------------------------------------------------------------------------
+# point query
+# ------------------------------------------------------------------------------------------------
+def test_query_fwd_vs_golden(net):
+    g = load_golden("query.npz")
+    feat, tmpx = O.synth_features(int(g["seed"]), B=2)
+    set_maps(net, feat, tmpx)
+    pts, cc = T(g["points"]), T(g["crop_center"])
+    outs, in_img = net.handle.query_fwd(*net._maps(), pts, cc, 15, want_in_img=True)
+    df, pca, parts, centers = outs
+    for name, got in (("df", df), ("pca", pca.view(2, 3, 3, -1)), ("parts", parts), ("centers", centers)):
+        assert rel_err(got, g[name]) < TOL, (name, rel_err(got, g[name]))
+    # bit-exact image-plane mask: the projection reproduces the reference's fp32 op order
+    proj = torch.from_numpy(g["proj"])
+    ref_in = (proj[:, 0] >= -1) & (proj[:, 0] <= 1) & (proj[:, 1] >= -1) & (proj[:, 1] <= 1)
+    assert torch.equal(in_img.cpu().bool(), ref_in)
+    assert torch.equal(df[:, 0].cpu() == O.OUT_DIST, ~ref_in)
+    n_diff, n_unclear = argmax_agrees(parts, torch.from_numpy(g["parts"]))
+    assert n_diff <= n_unclear
+
+
+def test_query_module_interface_and_grad_vs_golden(net):
+    g = load_golden("query.npz")
+    feat, tmpx = O.synth_features(int(g["seed"]), B=2)
+    set_maps(net, feat, tmpx)
+    cc = T(g["crop_center"])
+    p = T(g["points"]).clone().requires_grad_(True)
+    net.query(p, crop_center=cc)
+    df, pca, parts, centers = net.get_preds()
+    assert pca.shape == (2, 3, 3, 2048) and df.shape == (2, 2, 2048)
+    loss = (T(g["g_df"]) * df).sum() + (T(g["g_pca"]) * pca).sum() + (T(g["g_parts"]) * parts).sum() + \
+        (T(g["g_centers"]) * centers).sum()
+    loss.backward()
+    grad_close(p.grad, T(g["grad_all"]))
+    # the approx_surface pattern (recon/generator.py:63-70): clamp(df_h, max=2).sum().backward()
+    p2 = T(g["points"]).clone().requires_grad_(True)
+    net.query(p2, crop_center=cc)
+    torch.clamp(net.get_preds()[0][:, 0, :], max=2.0).sum().backward()
+    grad_close(p2.grad, T(g["grad_dfh"]))
+
+
+@pytest.mark.parametrize("B,N,kind", [(1, 1, "frustum"), (1, 31, "init_box"), (3, 33, "frustum"), (2, 100, "init_box"),
+                                      (1, 2049, "frustum"), (2, 20000, "init_box")])
+def test_query_ragged_sizes_vs_oracle(net, sd, B, N, kind):
+    feat, tmpx = O.synth_features(100 + N, B=B, hw=32)
+    set_maps(net, feat, tmpx)
+    cc = torch.tensor([[1008., 995.]]).repeat(B, 1) + torch.arange(B).float().view(B, 1) * 7
+    pts = O.synth_points(kind, N, B, N, cc)
+    with torch.no_grad():
+        ref = O.query(sd, feat, tmpx, pts, cc)
+    outs, in_img = net.handle.query_fwd(*net._maps(), pts.to(DEV), cc.to(DEV), 15, want_in_img=True)
+    for name, got, want in zip(("df", "pca", "parts", "centers"), outs, ref[:4]):
+        assert rel_err(got, want.reshape(got.shape)) < TOL, (name, rel_err(got, want.reshape(got.shape)))
+    assert torch.equal(in_img.cpu().bool(), ref[4])
+    g_df = torch.randn(B, 2, N, generator=torch.Generator().manual_seed(N))
+    g_c = torch.randn(B, 6, N, generator=torch.Generator().manual_seed(N + 1))
+    want_g = O.query_grad_points(sd, feat, tmpx, pts, cc, g_df=g_df, g_centers=g_c)
+    got_g = net.handle.query_bwd(*net._maps(), pts.to(DEV), cc.to(DEV), [g_df.to(DEV), None, None, g_c.to(DEV)])
+    grad_close(got_g, want_g)
+
+
+def test_query_empty_and_head_mask(net):
+    feat, tmpx = O.synth_features(7, B=1, hw=16)
+    set_maps(net, feat, tmpx)
+    cc = torch.tensor([[1008., 995.]], device=DEV)
+    outs, _ = net.handle.query_fwd(*net._maps(), torch.zeros(1, 0, 3, device=DEV), cc, 15)
+    assert outs[0].shape == (1, 2, 0)
+    pts = O.synth_points("frustum", 3, 1, 257).to(DEV)
+    full, _ = net.handle.query_fwd(*net._maps(), pts, cc, 15)
+    only_df, _ = net.handle.query_fwd(*net._maps(), pts, cc, 1)
+    assert only_df[1] is None and torch.equal(only_df[0], full[0])
+
+
+def test_query_grid_vs_oracle(net, sd):
+    """model/sdf.py:4-48 semantics: coordinates generated in-kernel == create_grid + query."""
+    feat, tmpx = O.synth_features(9, B=2, hw=32)
+    set_maps(net, feat, tmpx)
+    res, bmin, bmax = (12, 10, 9), [-3.0, -0.9, 0.2], [3.0, 1.8, 4.0]
+    coords = torch.from_numpy(O.create_grid(res, bmin, bmax).T.astype(np.float32)).unsqueeze(0)   # (1, XYZ, 3)
+    cc = torch.tensor([[1008., 995.], [990., 1010.]])
+    with torch.no_grad():
+        ref = O.query(sd, feat[1:2], tmpx[1:2], coords, cc[1:2])
+    outs = net.query_grid(res, bmin, bmax, cc, batch_index=1, head_mask=15, chunk=500)
+    for got, want in zip(outs, ref[:4]):
+        assert rel_err(got, want.reshape(got.shape)) < TOL
+    # chunking does not change a single bit
+    outs2 = net.query_grid(res, bmin, bmax, cc, batch_index=1, head_mask=15, chunk=1 << 20)
+    for a, b in zip(outs, outs2):
+        assert torch.equal(a, b)
+
+
+def test_query_permutation_equivariance_large(net):
+    """Size-independent property at production size: permuting 1M points permutes the outputs."""
+    feat, tmpx = O.synth_features(11, B=1)
+    set_maps(net, feat, tmpx)
+    N = 1 << 20
+    cc = torch.tensor([[1008., 995.]], device=DEV)
+    pts = O.synth_points("init_box", 5, 1, N).to(DEV)
+    perm = torch.randperm(N, generator=torch.Generator().manual_seed(1)).to(DEV)
+    a, ia = net.handle.query_fwd(*net._maps(), pts, cc, 15, want_in_img=True)
+    b, ib = net.handle.query_fwd(*net._maps(), pts[:, perm].contiguous(), cc, 15, want_in_img=True)
+    for x, y in zip(a, b):
+        assert torch.equal(x[:, :, perm], y)
+    assert torch.equal(ia[:, perm], ib)
+    frac_in = ia.float().mean().item()
+    assert 0.1 < frac_in < 0.5        # the init box puts ~24 % of the points in the image
+
+
+def test_approx_surface_vs_golden(net):
+    import chore_b200
+    g = load_golden("approx_surface.npz")
+    feat, tmpx = O.synth_features(int(g["seed"]), B=1)
+    set_maps(net, feat, tmpx)
+    gen = chore_b200.Generator(net, device=DEV)
+    cc = T(g["crop_center"])
+    for name in ("human", "object"):
+        s0 = O.synth_points("frustum", 32, 1, 512).to(DEV).requires_grad_(True)
+        samples, preds = gen.approx_surface(net, s0, 10, {"crop_center": cc}, name)
+        ref = T(g[f"samples_{name}"])
+        # ten chained gradient steps amplify rounding; compare in absolute metres
+        # The chain is chaotic on the white-noise test features: the ORACLE ITSELF, started from
+        # points perturbed by 1e-7 relative, keeps only ~87 % of the samples within 1e-3 after ten
+        # steps (measured on CPU).  So: tight on the median, loose on the tail; the single-step
+        # update is checked tightly below.
+        assert (samples.detach() - ref).abs().median() < 1e-5
+        assert ((samples.detach() - ref).abs().amax(-1) < 1e-3).float().mean() > 0.8
+    sd = O.make_state_dict(0, "unit")
+    s0 = O.synth_points("frustum", 32, 1, 512)
+    want, _ = O.approx_surface(sd, feat, tmpx, s0, cc.cpu(), 1, 1)
+    got, _ = gen.approx_surface(net, s0.to(DEV).requires_grad_(True), 1, {"crop_center": cc}, "object")
+    d = (got.detach().cpu() - want).abs().amax(-1)
+    assert d.median() < 1e-6 and (d < 1e-4).float().mean() > 0.995, (d.median(), (d < 1e-4).float().mean())
+
+
+# ------------------------------------------------------------------------------------------------
+# encoder
+# ------------------------------------------------------------------------------------------------
+def test_encoder_vs_golden_128(net):
+    g = load_golden("encoder_128.npz")
+    img = O.synth_images(int(g["seed"]), B=2, size=128).to(DEV)
+    net.filter(img)
+    feat, tmpx, normx = net.get_im_feat(), net.tmpx, net.normx
+    assert feat.shape == (2, 256, 32, 32) and tmpx.shape == (2, 64, 64, 64)
+    assert rel_err(tmpx, g["tmpx"]) < TOL, rel_err(tmpx, g["tmpx"])
+    assert rel_err(normx[:, :, ::4, ::4], g["normx"]) < TOL, rel_err(normx[:, :, ::4, ::4], g["normx"])
+    assert rel_err(feat, g["feat"]) < 5e-4, rel_err(feat, g["feat"])     # ~60 GN+conv layers deep
+
+
+def test_encoder_vs_golden_512(net):
+    g = load_golden("encoder_512.npz")
+    img = O.synth_images(int(g["seed"]), B=1, size=512).to(DEV)
+    net.filter(img)
+    feat, tmpx = net.get_im_feat(), net.tmpx
+    assert feat.shape == (1, 256, 128, 128) and tmpx.shape == (1, 64, 256, 256)
+    assert rel_err(tmpx[:, :, ::8, ::8], g["tmpx_s8"]) < TOL
+    assert rel_err(feat[:, :, ::8, ::8], g["feat_s8"]) < 5e-4, rel_err(feat[:, :, ::8, ::8], g["feat_s8"])
+    from oracle.make_golden import checksum
+    ck = checksum(feat.cpu().contiguous())
+    assert abs(ck[0] - g["feat_ck"][0]) < 1e-3 * abs(g["feat_ck"][2]) * feat.numel() ** 0.5
+
+
+def test_encoder_refinit_weights():
+    import chore_b200
+    g = load_golden("encoder_128_refinit.npz")
+    n = chore_b200.CHORE(device=DEV)
+    n.load_state_dict(O.make_state_dict(int(g["weights_seed"]), "ref_init"))
+    n.filter(O.synth_images(int(g["seed"]), B=1, size=128).to(DEV))
+    assert rel_err(n.tmpx, g["tmpx"]) < TOL
+    assert rel_err(n.get_im_feat(), g["feat"]) < 5e-4
+
+
+def test_encode_then_query_end_to_end(net, sd):
+    """filter() -> query() on the encoder's own channels-last maps == oracle encode + query."""
+    img = O.synth_images(77, B=1, size=128)
+    net.filter(img.to(DEV))
+    with torch.no_grad():
+        f, t = O.encode(sd, img)
+    cc = torch.tensor([[1008., 995.]])
+    pts = O.synth_points("frustum", 78, 1, 3000)
+    with torch.no_grad():
+        ref = O.query(sd, f, t, pts, cc)
+    net.query(pts.to(DEV), crop_center=cc.to(DEV))
+    for got, want in zip(net.get_preds(), ref[:4]):
+        assert rel_err(got, want) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# SMPL-H LBS, rigid transform, SO(3), fit step
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def smpl_layer():
+    import chore_b200
+    return chore_b200.SMPLHLayer(O.make_smplh_buffers(0), device=DEV)
+
+
+def test_lbs_vs_golden(smpl_layer):
+    g = load_golden("lbs.npz")
+    pose, betas, trans, offs = (T(g[k]).clone().requires_grad_(True) for k in ("pose", "betas", "trans", "offsets"))
+    verts, jtr, v_posed, naked = smpl_layer(pose, th_betas=betas, th_trans=trans, th_offsets=offs)
+    assert rel_err(verts, g["verts"]) < TOL and rel_err(jtr, g["jtr"]) < TOL
+    assert rel_err(v_posed[:, ::10], g["v_posed_s"]) < TOL and rel_err(naked[:, ::10], g["naked_s"]) < TOL
+    ((T(g["g_verts"]) * verts).sum() + (T(g["g_jtr"]) * jtr).sum()).backward()
+    assert rel_err(pose.grad, g["grad_pose"]) < 2e-4, rel_err(pose.grad, g["grad_pose"])
+    assert rel_err(betas.grad, g["grad_betas"]) < 2e-4, rel_err(betas.grad, g["grad_betas"])
+    assert rel_err(trans.grad, g["grad_trans"]) < 2e-4
+    assert rel_err(offs.grad[:, ::10], g["grad_offsets_s"]) < 2e-4
+
+
+def test_lbs_wrappers(smpl_layer):
+    import chore_b200
+    g = load_golden("lbs.npz")
+    w = chore_b200.SMPLPyTorchWrapperBatch(smpl_layer, 2, betas=T(g["betas"]), pose=T(g["pose"]), trans=T(g["trans"]),
+                                           offsets=T(g["offsets"]), device=DEV)
+    verts = w()[0]
+    assert rel_err(verts, g["verts"]) < TOL
+    split = chore_b200.SMPLPyTorchWrapperBatchSplitParams.from_smpl(w)
+    v2, j2, _, _ = split()
+    assert torch.equal(v2, verts)
+    (v2.sum() + j2.sum()).backward()
+    assert split.body_pose.grad is not None and split.top_betas.grad.abs().sum() > 0
+
+
+def test_rigid_and_so3_vs_golden():
+    import chore_b200
+    g = load_golden("rigid.npz")
+    fit = chore_b200.ReconFitterBehave(device=DEV)
+    R = fit.project_so3(T(g["rot"]))
+    assert rel_err(R, g["R"]) < 2e-5
+    assert rel_err(fit.project_so3(T(g["bad"])), g["R_bad"]) < 2e-5
+    moved = fit.transform_obj_verts(T(g["obj"]), T(g["R"]), T(g["t"]), T(g["s"]))
+    assert rel_err(moved, g["moved"]) < 2e-5
+
+
+def test_so3_backward_vs_torch_svd():
+    """the analytic adjoint of the projection == autograd through torch.svd (CPU, float64)."""
+    import chore_b200
+    gen = torch.Generator().manual_seed(5)
+    m = torch.eye(3).unsqueeze(0) + 0.3 * torch.randn(16, 3, 3, generator=gen)
+    gout = torch.randn(16, 3, 3, generator=gen)
+    md = m.double().requires_grad_(True)
+    (O.project_so3(md) * gout.double()).sum().backward()
+    mg = m.to(DEV).requires_grad_(True)
+    (chore_b200.ReconFitterBase.project_so3(mg) * gout.to(DEV)).sum().backward()
+    assert rel_err(mg.grad, md.grad.float()) < 1e-4, rel_err(mg.grad, md.grad.float())
+
+
+def test_fit_object_only_step_vs_golden(net):
+    import chore_b200
+    f = load_golden("fit_object_only.npz")
+    feat, tmpx = O.synth_features(int(f["seed"]), B=2)
+    set_maps(net, feat, tmpx)
+    fit = chore_b200.ReconFitterBehave(device=DEV)
+    rot, t, s = (T(f[k]).clone().requires_grad_(True) for k in ("rot", "t", "s"))
+    data = {"objects": T(f["obj"]), "query_dict": {"crop_center": T(f["crop_center"])}, "smpl_center": T(f["smpl_center"])}
+    losses = fit.forward_step(net, None, data, rot, t, s, "object only", noise=T(f["noise"]))
+    for k in ("object", "scale", "ocent"):
+        assert rel_err(losses[k], f[f"loss_{k}"]) < TOL, k
+    total = fit.sum_dict(losses, fit.get_loss_weights(), int(f["it"]))
+    assert rel_err(total, f["total"]) < TOL
+    total.backward()
+    assert rel_err(t.grad, f["grad_t"]) < 3e-4, rel_err(t.grad, f["grad_t"])
+    assert rel_err(s.grad, f["grad_s"]) < 3e-4
+    assert rel_err(rot.grad, f["grad_rot"]) < 3e-3      # through the SVD adjoint: ill-conditioned
+
+
+def test_smpl_fit_step_vs_oracle(net, sd, smpl_layer):
+    """LBS -> query -> df_h + part loss -> backward to (pose, betas, trans): one SMPL-phase step."""
+    import chore_b200
+    feat, tmpx = O.synth_features(61, B=1)
+    set_maps(net, feat, tmpx)
+    buf = O.make_smplh_buffers(0)
+    gen = torch.Generator().manual_seed(62)
+    pose0, betas0 = 0.1 * torch.randn(1, 156, generator=gen), 0.5 * torch.randn(1, 10, generator=gen)
+    trans0 = torch.tensor([[0.0, 0.1, 2.2]])
+    labels = torch.randint(14, (1, 6890), generator=gen)
+    cc = torch.tensor([[1008., 995.]])
+    # oracle
+    p, b, t = (x.clone().requires_grad_(True) for x in (pose0, betas0, trans0))
+    verts = O.lbs_forward(buf, p, b, t)[0]
+    lo = O.smpl_losses(sd, feat, tmpx, cc, verts, labels)
+    tot_o = O.sum_dict(lo, 1.0)
+    tot_o.backward()
+    # CUDA
+    w = chore_b200.SMPLPyTorchWrapperBatch(smpl_layer, 1, betas=betas0, pose=pose0, trans=trans0, device=DEV)
+    fit = chore_b200.ReconFitterBehave(device=DEV)
+    data = {"net": net, "query_dict": {"crop_center": cc.to(DEV)}, "part_labels": labels.to(DEV)}
+    lc = fit.forward_smpl(w, data)
+    tot_c = fit.sum_dict(lc, fit.get_loss_weights(), 1)
+    tot_c.backward()
+    # intermediate quantities first, so a failure says where it comes from
+    v_c = w()[0].detach()
+    assert rel_err(v_c, verts) < 1e-5, ("verts", rel_err(v_c, verts))
+    with torch.no_grad():
+        ref_q = O.query(sd, feat, tmpx, verts.detach(), cc)
+    got_q, got_in = net.handle.query_fwd(*net._maps(), verts.detach().to(DEV), cc.to(DEV), 15, want_in_img=True)
+    assert torch.equal(got_in.cpu().bool(), ref_q[4])
+    assert rel_err(got_q[0], ref_q[0]) < TOL, ("df on oracle verts", rel_err(got_q[0], ref_q[0]))
+    assert rel_err(lc["df_h"], lo["df_h"]) < TOL, (lc["df_h"].item(), lo["df_h"].item())
+    assert rel_err(lc["part"], lo["part"]) < TOL, (lc["part"].item(), lo["part"].item())
+    assert rel_err(tot_c, tot_o) < TOL
+    assert rel_err(w.trans.grad, t.grad) < 5e-4, rel_err(w.trans.grad, t.grad)
+    assert rel_err(w.betas.grad, b.grad) < 5e-4, rel_err(w.betas.grad, b.grad)
+    assert rel_err(w.pose.grad, p.grad) < 5e-4, rel_err(w.pose.grad, p.grad)
