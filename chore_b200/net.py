@@ -133,12 +133,13 @@ class CHORE(nn.Module):
         assert self.im_feat_list and self.tmpx is not None, "call filter(images) before query()"
         out = []
         for name, t in (("feat", self.im_feat_list[-1]), ("skip", self.tmpx)):
-            key = (name, t.data_ptr(), t._version, tuple(t.stride()))
+            # keyed on the tensor OBJECT (kept alive here, so its storage cannot be recycled for
+            # another map with the same address) and its version counter (in-place edits)
             hit = self._nhwc_cache.get(name)
-            if hit is None or hit[0] != key:
-                hit = (key, _to_nhwc(t.detach().to(self._device, torch.float32)))
+            if hit is None or hit[0] is not t or hit[1] != t._version:
+                hit = (t, t._version, _to_nhwc(t.detach().to(self._device, torch.float32)))
                 self._nhwc_cache[name] = hit
-            out.append(hit[1])
+            out.append(hit[2])
         return out[0], out[1]
 
     def project_points(self, points: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:

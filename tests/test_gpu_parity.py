@@ -169,30 +169,37 @@ def test_query_permutation_equivariance_large(net):
     assert 0.1 < frac_in < 0.5        # the init box puts ~24 % of the points in the image
 
 
-def test_approx_surface_vs_golden(net):
+def test_approx_surface_vs_golden(net, sd):
+    """Generator.approx_surface (recon/generator.py:50-79).
+
+    The 10-step chain is chaotic on the white-noise test features: the ORACLE ITSELF, restarted
+    from points perturbed by 1e-7 relative, ends with a median deviation of 7e-7 m (human field)
+    / 4e-3 m (object field) and only 87 % / 47 % of the samples within 1 mm (measured on CPU).
+    So the golden end points are compared loosely, and the trajectory is checked tightly step by
+    step with teacher forcing: every CUDA step starts from the oracle's samples of that step."""
     import chore_b200
     g = load_golden("approx_surface.npz")
     feat, tmpx = O.synth_features(int(g["seed"]), B=1)
     set_maps(net, feat, tmpx)
     gen = chore_b200.Generator(net, device=DEV)
     cc = T(g["crop_center"])
-    for name in ("human", "object"):
-        s0 = O.synth_points("frustum", 32, 1, 512).to(DEV).requires_grad_(True)
-        samples, preds = gen.approx_surface(net, s0, 10, {"crop_center": cc}, name)
-        ref = T(g[f"samples_{name}"])
-        # ten chained gradient steps amplify rounding; compare in absolute metres
-        # The chain is chaotic on the white-noise test features: the ORACLE ITSELF, started from
-        # points perturbed by 1e-7 relative, keeps only ~87 % of the samples within 1e-3 after ten
-        # steps (measured on CPU).  So: tight on the median, loose on the tail; the single-step
-        # update is checked tightly below.
-        assert (samples.detach() - ref).abs().median() < 1e-5
-        assert ((samples.detach() - ref).abs().amax(-1) < 1e-3).float().mean() > 0.8
-    sd = O.make_state_dict(0, "unit")
-    s0 = O.synth_points("frustum", 32, 1, 512)
-    want, _ = O.approx_surface(sd, feat, tmpx, s0, cc.cpu(), 1, 1)
-    got, _ = gen.approx_surface(net, s0.to(DEV).requires_grad_(True), 1, {"crop_center": cc}, "object")
-    d = (got.detach().cpu() - want).abs().amax(-1)
-    assert d.median() < 1e-6 and (d < 1e-4).float().mean() > 0.995, (d.median(), (d < 1e-4).float().mean())
+    s0 = O.synth_points("frustum", 32, 1, 512).to(DEV).requires_grad_(True)
+    samples, preds = gen.approx_surface(net, s0, 10, {"crop_center": cc}, "human")
+    d = (samples.detach() - T(g["samples_human"])).abs().amax(-1)
+    assert d.median() < 1e-5 and (d < 1e-3).float().mean() > 0.8, (d.median().item(), (d < 1e-3).float().mean().item())
+    assert preds[0].shape == (1, 2, 512) and samples.requires_grad
+    for k, name in enumerate(("human", "object")):
+        cur = O.synth_points("frustum", 32, 1, 512)
+        for step in range(10):
+            nxt, _ = O.approx_surface(sd, feat, tmpx, cur, cc.cpu(), 1, k)
+            got, _ = gen.approx_surface(net, cur.to(DEV).requires_grad_(True), 1, {"crop_center": cc}, name)
+            d = (got.detach().cpu() - nxt).abs().amax(-1)
+            # a point whose gradient is ~0 has an ill-defined direction: allow a sliver of outliers
+            assert d.median() < 2e-6 and (d < 1e-4).float().mean() > 0.99, (name, step, d.median().item(), (d < 1e-4).float().mean().item())
+            cur = nxt
+    if int(g["seed"]) == 31:        # the teacher-forced chain reproduces the golden end points
+        assert (cur - torch.from_numpy(g["samples_object"])).abs().max() < 1e-3
+
 
 
 # ------------------------------------------------------------------------------------------------
@@ -307,7 +314,16 @@ def test_so3_backward_vs_torch_svd():
     assert rel_err(mg.grad, md.grad.float()) < 1e-4, rel_err(mg.grad, md.grad.float())
 
 
-def test_fit_object_only_step_vs_golden(net):
+def test_fit_object_only_step_vs_golden(net, sd):
+    """forward_step(phase='object only') (recon/recon_fit_behave.py:165-198): loss terms against the
+    golden of the live reference, gradients stage by stage.
+
+    Why stage by stage: the reference projects to SO(3) with an fp32 LAPACK SVD whose R differs from
+    the fp64 in-kernel projection by ~1e-5, i.e. the object points move by ~2e-6 m.  On white-noise
+    feature maps the per-point gradient is discontinuous across texel borders (bilinear), so a few
+    points per thousand get a different gradient, and the parameter gradients -- sums of 3000
+    per-point terms of both signs -- inherit that.  With identical points the per-point gradients
+    agree to 1e-6 (first block); the chain is then checked with the oracle's R."""
     import chore_b200
     f = load_golden("fit_object_only.npz")
     feat, tmpx = O.synth_features(int(f["seed"]), B=2)
@@ -321,13 +337,48 @@ def test_fit_object_only_step_vs_golden(net):
     total = fit.sum_dict(losses, fit.get_loss_weights(), int(f["it"]))
     assert rel_err(total, f["total"]) < TOL
     total.backward()
-    assert rel_err(t.grad, f["grad_t"]) < 3e-4, rel_err(t.grad, f["grad_t"])
-    assert rel_err(s.grad, f["grad_s"]) < 3e-4
-    assert rel_err(rot.grad, f["grad_rot"]) < 3e-3      # through the SVD adjoint: ill-conditioned
+    for name, got, tol in (("t", t.grad, 5e-2), ("s", s.grad, 5e-2), ("rot", rot.grad, 1e-1)):
+        assert rel_err(got, f[f"grad_{name}"]) < tol, (name, rel_err(got, f[f"grad_{name}"]))
+
+    def losses_of(query, obj, sc, s_):
+        cen = query(obj)[3]
+        df = query(obj)[0]            # queried twice in the reference
+        return {"object": torch.clamp(df[:, 1:2, :], max=0.8).mean(), "scale": torch.mean((s_ - 1.0) ** 2),
+                "ocent": torch.nn.functional.mse_loss(torch.mean(obj, 1), sc + torch.mean(cen[:, 3:, :], -1),
+                                                      reduction="none").sum(-1).mean()}
+
+    def q_cuda(obj):
+        net.query(obj, **data["query_dict"])
+        return net.get_preds()
+
+    # oracle chain (CPU), keeping R and the per-point gradient
+    ro, to, so = (torch.from_numpy(f[k]).clone().requires_grad_(True) for k in ("rot", "t", "s"))
+    R_o = O.decopose_axis(ro, torch.from_numpy(f["noise"]))
+    R_o.retain_grad()
+    obj_o = O.transform_obj_verts(torch.from_numpy(f["obj"]), R_o, to, so)
+    obj_o.retain_grad()
+    cc_o, sc_o = torch.from_numpy(f["crop_center"]), torch.from_numpy(f["smpl_center"])
+    O.sum_dict(losses_of(lambda o: O.query(sd, feat, tmpx, o, cc_o), obj_o, sc_o, so), float(f["it"])).backward()
+    # (1) identical points: per-point gradient of the whole loss
+    p_c = obj_o.detach().contiguous().to(DEV).requires_grad_(True)
+    fit.sum_dict(losses_of(q_cuda, p_c, data["smpl_center"], T(f["s"])), fit.get_loss_weights(), int(f["it"])).backward()
+    grad_close(p_c.grad, obj_o.grad, tol=2e-5, frac=0.999, worst=0.5)
+    # (2) identical R: rigid transform + queries + losses, gradients to (R, t, s)
+    R_c = R_o.detach().to(DEV).requires_grad_(True)
+    t2, s2 = (T(f[k]).clone().requires_grad_(True) for k in ("t", "s"))
+    obj_c = fit.transform_obj_verts(data["objects"], R_c, t2, s2)
+    assert rel_err(obj_c, obj_o) < 1e-6
+    fit.sum_dict(losses_of(q_cuda, obj_c, data["smpl_center"], s2), fit.get_loss_weights(), int(f["it"])).backward()
+    one_point = 2.0 * obj_o.grad.abs().amax().item() * 1.5       # two texel-border crossings
+    for name, got, want in (("R", R_c.grad, R_o.grad), ("t", t2.grad, to.grad), ("s", s2.grad, so.grad)):
+        bound = 2e-4 * (want.abs() + want.pow(2).mean().sqrt()) + one_point
+        assert bool(((got.cpu() - want).abs() <= bound).all()), (name, (got.cpu() - want).abs().max().item(), one_point)
 
 
 def test_smpl_fit_step_vs_oracle(net, sd, smpl_layer):
-    """LBS -> query -> df_h + part loss -> backward to (pose, betas, trans): one SMPL-phase step."""
+    """LBS -> query -> df_h + part loss -> backward to (pose, betas, trans): one SMPL-phase step
+    (recon/recon_fit_behave.py:293-337 field terms).  Losses end to end; gradients stage by stage
+    (see test_fit_object_only_step_vs_golden for why)."""
     import chore_b200
     feat, tmpx = O.synth_features(61, B=1)
     set_maps(net, feat, tmpx)
@@ -340,27 +391,33 @@ def test_smpl_fit_step_vs_oracle(net, sd, smpl_layer):
     # oracle
     p, b, t = (x.clone().requires_grad_(True) for x in (pose0, betas0, trans0))
     verts = O.lbs_forward(buf, p, b, t)[0]
+    verts.retain_grad()
     lo = O.smpl_losses(sd, feat, tmpx, cc, verts, labels)
     tot_o = O.sum_dict(lo, 1.0)
     tot_o.backward()
-    # CUDA
+    # CUDA, end to end through the wrappers
     w = chore_b200.SMPLPyTorchWrapperBatch(smpl_layer, 1, betas=betas0, pose=pose0, trans=trans0, device=DEV)
     fit = chore_b200.ReconFitterBehave(device=DEV)
     data = {"net": net, "query_dict": {"crop_center": cc.to(DEV)}, "part_labels": labels.to(DEV)}
     lc = fit.forward_smpl(w, data)
     tot_c = fit.sum_dict(lc, fit.get_loss_weights(), 1)
     tot_c.backward()
-    # intermediate quantities first, so a failure says where it comes from
-    v_c = w()[0].detach()
-    assert rel_err(v_c, verts) < 1e-5, ("verts", rel_err(v_c, verts))
-    with torch.no_grad():
-        ref_q = O.query(sd, feat, tmpx, verts.detach(), cc)
-    got_q, got_in = net.handle.query_fwd(*net._maps(), verts.detach().to(DEV), cc.to(DEV), 15, want_in_img=True)
-    assert torch.equal(got_in.cpu().bool(), ref_q[4])
-    assert rel_err(got_q[0], ref_q[0]) < TOL, ("df on oracle verts", rel_err(got_q[0], ref_q[0]))
+    assert rel_err(w()[0], verts) < 1e-5
     assert rel_err(lc["df_h"], lo["df_h"]) < TOL, (lc["df_h"].item(), lo["df_h"].item())
     assert rel_err(lc["part"], lo["part"]) < TOL, (lc["part"].item(), lo["part"].item())
     assert rel_err(tot_c, tot_o) < TOL
-    assert rel_err(w.trans.grad, t.grad) < 5e-4, rel_err(w.trans.grad, t.grad)
-    assert rel_err(w.betas.grad, b.grad) < 5e-4, rel_err(w.betas.grad, b.grad)
-    assert rel_err(w.pose.grad, p.grad) < 5e-4, rel_err(w.pose.grad, p.grad)
+    for got, want in ((w.trans.grad, t.grad), (w.betas.grad, b.grad), (w.pose.grad, p.grad)):
+        assert rel_err(got, want) < 1e-1
+    # stage 1: identical vertices -> per-vertex gradient of the field losses
+    v_c = verts.detach().contiguous().to(DEV).requires_grad_(True)
+    net.query(v_c, crop_center=cc.to(DEV))
+    df_c, _, parts_c, _ = net.get_preds()
+    l1 = {"df_h": torch.clamp(df_c[:, 0:1, :], max=0.1).mean(),
+          "part": torch.nn.functional.cross_entropy(parts_c, labels.to(DEV), reduction="none").sum(-1).mean()}
+    fit.sum_dict(l1, fit.get_loss_weights(), 1).backward()
+    grad_close(v_c.grad, verts.grad, tol=2e-5, frac=0.999, worst=0.5)
+    # stage 2: identical vertex gradients -> LBS adjoint
+    g_pose, g_betas, g_trans, _ = smpl_layer.handle.lbs_bwd(pose0.to(DEV), betas0.to(DEV), trans0.to(DEV), None,
+                                                            verts.grad.contiguous().to(DEV), None, False)
+    assert rel_err(g_trans, t.grad) < 2e-4 and rel_err(g_betas, b.grad) < 2e-4, (rel_err(g_trans, t.grad), rel_err(g_betas, b.grad))
+    assert rel_err(g_pose, p.grad) < 2e-4, rel_err(g_pose, p.grad)
