@@ -59,6 +59,7 @@ struct MlpWeights {
     float *w3t = nullptr, *w3o = nullptr, *b3 = nullptr;
     float *w4 = nullptr;    // [4][16][128]  rows >= n_out zero
     float *b4 = nullptr;    // [4][16]
+    unsigned char *wstream = nullptr;   // tensor-core path: per-tile stream of pre-swizzled fp16 hi/lo panels
     bool loaded = false;
 };
 
@@ -112,6 +113,15 @@ int chore_ws_reserve(chore_handle *h, size_t bytes);    // (re)allocates h->ws
 int chore_ws2_reserve(chore_handle *h, size_t bytes);   // (re)allocates h->ws2
 int chore_lbs_ws_reserve(chore_handle *h, size_t bytes);
 int chore_dev_alloc(chore_handle *h, void **p, size_t bytes);
+
+// tensor-core query path (query_tc.cu)
+int query_tc_pack_weights(chore_handle *h, const std::vector<float> &w1, const std::vector<float> &w2,
+                          const std::vector<float> &w3);
+int query_tc_launch(chore_handle *h, const float *feat, const float *skip, int fh, int fw, const float *points,
+                    const float *crop_center, int B, long long N, long long n_start, long long n_count, int grid_mode,
+                    int batch_index, const int *res, const double *step, const double *bmin, unsigned head_mask,
+                    float *const outs[4], unsigned char *in_img, cudaStream_t st);
+bool query_use_tensor_cores();   // CHORE_B200_QUERY=simt selects the fp32 SIMT kernel
 
 // implemented per translation unit
 int query_load_weights(chore_handle *h, const std::map<std::string, const chore_tensor_desc *> &t);

@@ -12,6 +12,7 @@
 // is staged once in shared memory (Xt[k][p]) and the four heads run as register-tiled fp32
 // GEMMs against weight panels streamed with cp.async (L2-resident, 1.2 MB in total).
 #include "common.cuh"
+#include <cstdlib>
 #include <cstring>
 
 namespace {
@@ -573,6 +574,7 @@ int query_load_weights(chore_handle *h, const std::map<std::string, const chore_
     std::vector<float> w1t((size_t)kPointCPad * 512, 0.f), w1o((size_t)512 * kW1oLd, 0.f), b1(512, 0.f);
     std::vector<float> w2t((size_t)4 * 128 * 128), w2o(w2t.size()), b2(512), w3t(w2t.size()), w3o(w2t.size()), b3(512);
     std::vector<float> w4((size_t)4 * 16 * 128, 0.f), b4(64, 0.f), tmp;
+    std::vector<float> raw1((size_t)4 * 128 * kPointC), raw2((size_t)4 * 128 * 128), raw3((size_t)4 * 128 * 128);
     for (int hd = 0; hd < kNumHeads; ++hd) {
         const std::string hn = head_names[hd];
         const chore_tensor_desc *d = t.at(hn + ".0.weight");
@@ -581,6 +583,7 @@ int query_load_weights(chore_handle *h, const std::map<std::string, const chore_
         for (int o = 0; o < kHidden; ++o)
             for (int k = 0; k < kPointC; ++k) {
                 const float v = tmp[(size_t)o * kPointC + k];
+                raw1[((size_t)hd * kHidden + o) * kPointC + k] = v;
                 w1t[(size_t)k * 512 + hd * kHidden + o] = v;
                 w1o[(size_t)(hd * kHidden + o) * kW1oLd + k] = v;
             }
@@ -595,6 +598,7 @@ int query_load_weights(chore_handle *h, const std::map<std::string, const chore_
             for (int o = 0; o < kHidden; ++o)
                 for (int k = 0; k < kHidden; ++k) {
                     const float v = tmp[(size_t)o * kHidden + k];
+                    (layer == 0 ? raw2 : raw3)[((size_t)hd * kHidden + o) * kHidden + k] = v;
                     wt[((size_t)hd * kHidden + k) * kHidden + o] = v;
                     wo[((size_t)hd * kHidden + o) * kHidden + k] = v;
                 }
@@ -617,8 +621,17 @@ int query_load_weights(chore_handle *h, const std::map<std::string, const chore_
     rc |= upload(h, &m.w3t, w3t); rc |= upload(h, &m.w3o, w3o); rc |= upload(h, &m.b3, b3);
     rc |= upload(h, &m.w4, w4); rc |= upload(h, &m.b4, b4);
     if (rc) return CHORE_ERR_CUDA;
+    if (int rc2 = query_tc_pack_weights(h, raw1, raw2, raw3)) return rc2;
     m.loaded = true;
     return CHORE_OK;
+}
+
+bool query_use_tensor_cores() {
+    static const bool simt = [] {
+        const char *e = getenv("CHORE_B200_QUERY");
+        return e != nullptr && strcmp(e, "simt") == 0;
+    }();
+    return !simt;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -644,6 +657,9 @@ extern "C" int chore_query_fwd(chore_handle *h, const float *feat, const float *
     q.in_img = in_img;
     fill_weights(q, h->mlp);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (query_use_tensor_cores())
+        return query_tc_launch(h, feat, skip, fh, fw, points, crop_center, B, N, 0, N, 0, 0, nullptr, nullptr, nullptr,
+                               head_mask, outs, in_img, st);
     // small problems: 32-point tiles fill more SMs
     const long long tiles64 = ((long long)N + 63) / 64 * B;
     if (tiles64 < 2ll * h->sm_count) return launch_fwd<32>(q, B, st);
@@ -680,6 +696,9 @@ extern "C" int chore_query_grid(chore_handle *h, const float *feat, const float 
     for (int i = 0; i < kNumHeads; ++i) q.out[i] = outs[i] ? outs[i] - (size_t)b * kHeadOut[i] * total : nullptr;
     q.in_img = nullptr;
     fill_weights(q, h->mlp);
+    if (query_use_tensor_cores())
+        return query_tc_launch(h, feat, skip, fh, fw, nullptr, crop_center, 1, total, start, count, 1, b, res, q.step, q.bmin,
+                               head_mask, q.out, nullptr, static_cast<cudaStream_t>(stream));
     return launch_fwd<64>(q, 1, static_cast<cudaStream_t>(stream));
 }
 

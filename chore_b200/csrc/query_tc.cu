@@ -1,0 +1,610 @@
+// Fused point query on the 5th-generation tensor cores (tcgen05 + TMEM), forward only.
+//
+// Same contract as query_fwd_kernel (query.cu) -- projection, two bilinear gathers, 4-head MLP,
+// OUT_DIST mask, reference output layouts -- but the three 128-wide layers of every head run as
+// tcgen05.mma (kind::f16, M=128 points x N=128 channels x K=16 per instruction) with fp32
+// accumulators in tensor memory.
+//
+// fp32-faithful math on fp16 tensor cores: every operand is split x = hi + lo with
+// hi = fp16(x), lo = fp16(x - hi) (22 significant bits), and a product is evaluated as
+// hi*hi + lo*hi + hi*lo with fp32 accumulation: three MMAs per logical MMA, error ~2^-22 per
+// term, i.e. the same order as an fp32 FMA chain (the dropped lo*lo term is 2^-22 relative).
+//
+// One persistent CTA per SM, 14 warps, everything synchronised with mbarriers:
+//   warp 0      weight producer: cp.async.bulk of pre-swizzled 16 KB weight panels (the whole
+//               1.25 MB weight stream is re-read from L2 once per 128-point tile)
+//   warp 1      MMA issuer (one elected lane), owns the TMEM allocation (512 columns:
+//               one 128x128 fp32 accumulator per head)
+//   warps 2-5   gather: projection + bilinear taps -> A operand k-blocks (64 channels, hi/lo
+//               fp16, 128B-swizzled K-major) in a 2-stage ring
+//   warps 6-13  epilogue: TMEM -> registers, bias + ReLU, hi/lo split -> activation k-blocks
+//               (A operand of the next layer, 3-stage ring); after layer 3 the last (<=14-wide)
+//               layer is evaluated in fp32 on the CUDA cores and written to HBM
+//
+// Per tile the issue order is L1(kb, head) for 6 k-blocks x 4 heads (all four accumulators
+// live), then L2(head), L3(head); epilogues of one head overlap the MMAs of the others.
+#include "common.cuh"
+
+#include <cuda_fp16.h>
+#include <cstring>
+
+namespace {
+
+constexpr int kTileM = 128;                  // points per tile = TMEM lanes
+constexpr int kKB = 64;                      // channels per k-block (one 128 B swizzle atom of fp16)
+constexpr int kPanelBytes = kTileM * kKB * 2;          // 16 KB: 128 rows x 64 fp16
+constexpr int kStageA = 2 * kPanelBytes;               // hi + lo
+constexpr int kNA = 2, kNACT = 3, kNW = 4;             // ring depths
+constexpr int kL1Blocks = 6;                 // 4 x feat(64) | skip(64) | xyz(3, one k-step)
+constexpr int kUnitsPerTile = kL1Blocks * 4 * 2 + 2 * (4 * 2 * 2);   // 48 + 32 = 80 weight panels
+constexpr int kThreads = 14 * 32;
+constexpr int kGatherWarp0 = 2, kEpiWarp0 = 6;
+constexpr size_t kSmemBytes = 1024 + (size_t)kNA * kStageA + (size_t)kNACT * kStageA + (size_t)kNW * kPanelBytes + 512;
+
+constexpr float kFx = static_cast<float>(979.7844 / 2048. * 2048);
+constexpr float kFy = static_cast<float>(979.840 / 2048. * 2048);
+constexpr float kCx = static_cast<float>(1018.952 / 2048. * 2048);
+constexpr float kCy = static_cast<float>(779.486 / 2048. * 2048);
+
+struct TcParams {
+    const float *feat, *skip;
+    int fh, fw;
+    const float *points;
+    const float *crop_center;
+    int B;
+    long long N, n_start, n_count;
+    int grid_mode, ry, rz, batch_index;
+    double step[3], bmin[3];
+    unsigned head_mask;
+    float *out[4];
+    unsigned char *in_img;
+    const unsigned char *wstream;     // kUnitsPerTile x 16 KB pre-swizzled fp16 panels
+    const float *b1, *b2, *b3;        // [4][128]
+    const float *w4, *b4;             // [4][16][128], [4][16] fp32
+    long long tiles_per_b, total_tiles;
+};
+
+__host__ __device__ __forceinline__ int head_out_tc(int h) { return h == 0 ? 2 : (h == 1 ? 9 : (h == 2 ? 14 : 6)); }
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    // the suspend-time hint lets the hardware park the warp instead of burning issue slots in a spin loop
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// bulk async copy global -> shared, completion counted on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);          // start address
+    d |= (uint64_t)1 << 16;                          // leading byte offset (ignored for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset: 8 rows x 128 B
+    d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: kind::f16, A = B = F16, D = F32, both K-major, M x N
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// x = hi + lo, both fp16 (clamped to the fp16 range); packs two consecutive values
+__device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo) {
+    a = fminf(fmaxf(a, -65504.f), 65504.f);
+    b = fminf(fmaxf(b, -65504.f), 65504.f);
+    const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
+    const __half la = __float2half_rn(a - __half2float(ha)), lb = __float2half_rn(b - __half2float(hb));
+    hi = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
+    lo = (uint32_t)__half_as_ushort(la) | ((uint32_t)__half_as_ushort(lb) << 16);
+}
+
+// byte offset of 16-byte chunk `c` (8 fp16) of row `r` inside a 128B-swizzled K-major panel
+__device__ __forceinline__ uint32_t sw128(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+
+// ---------------------------------------------------------------------------------------------
+// point source + projection (exact fp32 op order of model/camera.py:64-65,75-78)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_point(const TcParams &q, int b, long long n, float &x, float &y, float &z) {
+    if (q.grid_mode) {
+        const long long g = q.n_start + n;
+        long long ix, iy, iz;
+        if (g < 0x7fffffffll) {          // 32-bit division is ~5x cheaper than the 64-bit sequence
+            const unsigned g32 = (unsigned)g, t32 = g32 / (unsigned)q.rz;
+            iz = g32 - t32 * (unsigned)q.rz;
+            const unsigned x32 = t32 / (unsigned)q.ry;
+            iy = t32 - x32 * (unsigned)q.ry; ix = x32;
+        } else {
+            iz = g % q.rz;
+            const long long t = g / q.rz;
+            iy = t % q.ry; ix = t / q.ry;
+        }
+        x = (float)__dadd_rn(__dmul_rn(q.step[0], (double)ix), q.bmin[0]);
+        y = (float)__dadd_rn(__dmul_rn(q.step[1], (double)iy), q.bmin[1]);
+        z = (float)__dadd_rn(__dmul_rn(q.step[2], (double)iz), q.bmin[2]);
+    } else {
+        const float *p = q.points + ((size_t)b * q.N + q.n_start + n) * 3;
+        x = __ldg(p); y = __ldg(p + 1); z = __ldg(p + 2);
+    }
+}
+__device__ __forceinline__ void project_tc(float x, float y, float z, float ccx, float ccy, float &nx, float &ny) {
+    float px = __fadd_rn(__fdiv_rn(__fmul_rn(kFx, x), z), kCx);
+    float py = __fadd_rn(__fdiv_rn(__fmul_rn(kFy, y), z), kCy);
+    px = __fsub_rn(__fadd_rn(600.0f, px), ccx);
+    py = __fsub_rn(__fadd_rn(600.0f, py), ccy);
+    nx = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, px), 1200.0f), 1.0f);
+    ny = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, py), 1200.0f), 1.0f);
+}
+struct TapsTc {
+    int x0, y0;
+    float w[4];        // nw, ne, sw, se weights (0 for out-of-range taps)
+    unsigned valid;
+};
+__device__ __forceinline__ TapsTc make_taps_tc(float nx, float ny, int H, int W) {
+    TapsTc t;
+    const float ix = __fmul_rn(__fadd_rn(nx, 1.0f), 0.5f * (float)(W - 1));
+    const float iy = __fmul_rn(__fadd_rn(ny, 1.0f), 0.5f * (float)(H - 1));
+    t.valid = 0; t.x0 = 0; t.y0 = 0;
+    t.w[0] = t.w[1] = t.w[2] = t.w[3] = 0.f;
+    if (ix > -1.0f && ix < (float)W && iy > -1.0f && iy < (float)H) {
+        const float fx0 = floorf(ix), fy0 = floorf(iy);
+        t.x0 = (int)fx0; t.y0 = (int)fy0;
+        const float wx = ix - fx0, wy = iy - fy0;
+        const bool xl = t.x0 >= 0, xr = t.x0 + 1 < W, yt = t.y0 >= 0, yb = t.y0 + 1 < H;
+        t.valid = (unsigned)(xl && yt) | ((unsigned)(xr && yt) << 1) | ((unsigned)(xl && yb) << 2) | ((unsigned)(xr && yb) << 3);
+        t.w[0] = (1.f - wy) * (1.f - wx); t.w[1] = (1.f - wy) * wx; t.w[2] = wy * (1.f - wx); t.w[3] = wy * wx;
+    }
+    return t;
+}
+
+struct Bars {
+    uint64_t a_full[kNA], a_empty[kNA];
+    uint64_t w_full[kNW], w_empty[kNW];
+    uint64_t act_full[kNACT], act_empty[kNACT];
+    uint64_t tm_full[4], tm_empty[4];
+    uint32_t tmem_base;
+};
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1) query_tc_kernel(const TcParams q) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *ringA = smem;                                      // [kNA][hi 16K | lo 16K]
+    uint8_t *ringAct = ringA + (size_t)kNA * kStageA;           // [kNACT][hi 16K | lo 16K]
+    uint8_t *ringW = ringAct + (size_t)kNACT * kStageA;         // [kNW][16K]
+    Bars *bars = reinterpret_cast<Bars *>(ringW + (size_t)kNW * kPanelBytes);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kNA; ++i) { mbar_init(&bars->a_full[i], 4); mbar_init(&bars->a_empty[i], 1); }
+        for (int i = 0; i < kNW; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
+        for (int i = 0; i < kNACT; ++i) { mbar_init(&bars->act_full[i], 4); mbar_init(&bars->act_empty[i], 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&bars->tm_full[i], 1); mbar_init(&bars->tm_empty[i], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {   // TMEM: all 512 columns (4 heads x 128 fp32 accumulator columns)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&bars->tmem_base)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    const long long first_tile = blockIdx.x, tile_stride = gridDim.x;
+
+    if (warp == 0) {
+        // =============================== weight producer ===============================
+        if (lane == 0) {
+            uint32_t u = 0;   // running panel counter over all tiles
+            for (long long tile = first_tile; tile < q.total_tiles; tile += tile_stride) {
+                for (int i = 0; i < kUnitsPerTile; ++i, ++u) {
+                    const int s = u % kNW;
+                    const uint32_t ph = (u / kNW) & 1;
+                    mbar_wait(&bars->w_empty[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&bars->w_full[s], kPanelBytes);
+                    bulk_g2s(ringW + (size_t)s * kPanelBytes, q.wstream + (size_t)i * kPanelBytes, kPanelBytes, &bars->w_full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =============================== MMA issuer ===============================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(kTileM, 128);
+            uint32_t u = 0;        // weight panel counter
+            uint32_t ablk = 0;     // A ring block counter
+            uint32_t actblk = 0;   // activation ring block counter
+            uint32_t tile_i = 0;
+            for (long long tile = first_tile; tile < q.total_tiles; tile += tile_stride, ++tile_i) {
+                // ---- layer 1: 6 k-blocks x 4 heads, all four accumulators live ----
+                for (int kb = 0; kb < kL1Blocks; ++kb, ++ablk) {
+                    const int sa = ablk % kNA;
+                    mbar_wait(&bars->a_full[sa], (ablk / kNA) & 1);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(ringA + (size_t)sa * kStageA), a_lo = a_hi + kPanelBytes;
+                    const int ksteps = kb == kL1Blocks - 1 ? 1 : 4;     // the xyz block holds 16 channels
+                    for (int h = 0; h < 4; ++h) {
+                        if (kb == 0) {   // accumulator of head h must have been drained (previous tile)
+                            mbar_wait(&bars->tm_empty[h], (tile_i & 1) ^ 1);
+                            tc_fence_after();
+                        }
+                        const uint32_t d = tmem_base + h * 128;
+                        {   // panel w_hi: a_hi*w_hi + a_lo*w_hi
+                            const int s = u % kNW;
+                            mbar_wait(&bars->w_full[s], (u / kNW) & 1);
+                            tc_fence_after();
+                            const uint32_t wb = smem_u32(ringW + (size_t)s * kPanelBytes);
+                            for (int ks = 0; ks < ksteps; ++ks) {
+                                umma_f16(d, make_desc(a_hi + ks * 32), make_desc(wb + ks * 32), idesc, (kb | ks) != 0);
+                                umma_f16(d, make_desc(a_lo + ks * 32), make_desc(wb + ks * 32), idesc, 1);
+                            }
+                            umma_commit(&bars->w_empty[s]);
+                            ++u;
+                        }
+                        {   // panel w_lo: a_hi*w_lo
+                            const int s = u % kNW;
+                            mbar_wait(&bars->w_full[s], (u / kNW) & 1);
+                            tc_fence_after();
+                            const uint32_t wb = smem_u32(ringW + (size_t)s * kPanelBytes);
+                            for (int ks = 0; ks < ksteps; ++ks) umma_f16(d, make_desc(a_hi + ks * 32), make_desc(wb + ks * 32), idesc, 1);
+                            umma_commit(&bars->w_empty[s]);
+                            ++u;
+                        }
+                        if (kb == kL1Blocks - 1) umma_commit(&bars->tm_full[h]);   // layer-1 accumulator of head h complete
+                    }
+                    umma_commit(&bars->a_empty[sa]);
+                }
+                // ---- layers 2 and 3: per head, A operand = activation blocks written by the epilogue ----
+                for (int layer = 0; layer < 2; ++layer) {
+                    for (int h = 0; h < 4; ++h) {
+                        const uint32_t d = tmem_base + h * 128;
+                        // both activation blocks must be complete before the accumulator is overwritten
+                        const uint32_t b0 = actblk, b1 = actblk + 1;
+                        mbar_wait(&bars->act_full[b0 % kNACT], (b0 / kNACT) & 1);
+                        mbar_wait(&bars->act_full[b1 % kNACT], (b1 / kNACT) & 1);
+                        tc_fence_after();
+                        for (int kb = 0; kb < 2; ++kb, ++actblk) {
+                            const int sa = actblk % kNACT;
+                            const uint32_t a_hi = smem_u32(ringAct + (size_t)sa * kStageA), a_lo = a_hi + kPanelBytes;
+                            {
+                                const int s = u % kNW;
+                                mbar_wait(&bars->w_full[s], (u / kNW) & 1);
+                                tc_fence_after();
+                                const uint32_t wb = smem_u32(ringW + (size_t)s * kPanelBytes);
+                                for (int ks = 0; ks < 4; ++ks) {
+                                    umma_f16(d, make_desc(a_hi + ks * 32), make_desc(wb + ks * 32), idesc, (kb | ks) != 0);
+                                    umma_f16(d, make_desc(a_lo + ks * 32), make_desc(wb + ks * 32), idesc, 1);
+                                }
+                                umma_commit(&bars->w_empty[s]);
+                                ++u;
+                            }
+                            {
+                                const int s = u % kNW;
+                                mbar_wait(&bars->w_full[s], (u / kNW) & 1);
+                                tc_fence_after();
+                                const uint32_t wb = smem_u32(ringW + (size_t)s * kPanelBytes);
+                                for (int ks = 0; ks < 4; ++ks) umma_f16(d, make_desc(a_hi + ks * 32), make_desc(wb + ks * 32), idesc, 1);
+                                umma_commit(&bars->w_empty[s]);
+                                ++u;
+                            }
+                            umma_commit(&bars->act_empty[sa]);
+                        }
+                        umma_commit(&bars->tm_full[h]);
+                    }
+                }
+            }
+        }
+    } else if (warp < kEpiWarp0) {
+        // =============================== gather warps ===============================
+        // warp g owns rows [32g, 32g+32); a half-warp handles one point: 16 lanes x 4 channels = one 64-channel k-block
+        const int g = warp - kGatherWarp0;
+        const int half = lane >> 4, l16 = lane & 15;
+        uint32_t ablk = 0;
+        for (long long tile = first_tile; tile < q.total_tiles; tile += tile_stride) {
+            const int b = q.grid_mode ? q.batch_index : (int)(tile / q.tiles_per_b);
+            const long long n0 = (tile % q.tiles_per_b) * kTileM;
+            const float ccx = __ldg(q.crop_center + b * 2), ccy = __ldg(q.crop_center + b * 2 + 1);
+            const float *F = q.feat + (size_t)b * q.fh * q.fw * kFeatC;
+            const float *S = q.skip + (size_t)b * (2 * q.fh) * (2 * q.fw) * kSkipC;
+            // lane L projects row 32g + L once per tile; the k-block loop fetches it with shuffles
+            float my_x = 0.f, my_y = 0.f, my_z = 1.f, my_nx, my_ny;
+            if (n0 + g * 32 + lane < q.n_count) load_point(q, b, n0 + g * 32 + lane, my_x, my_y, my_z);
+            project_tc(my_x, my_y, my_z, ccx, ccy, my_nx, my_ny);
+            for (int kb = 0; kb < kL1Blocks; ++kb, ++ablk) {
+                const int sa = ablk % kNA;
+                mbar_wait(&bars->a_empty[sa], ((ablk / kNA) & 1) ^ 1);
+                uint8_t *hi = ringA + (size_t)sa * kStageA, *lo = hi + kPanelBytes;
+                if (kb < 5) {
+                    const bool is_feat = kb < 4;
+                    const int H = is_feat ? q.fh : 2 * q.fh, W = is_feat ? q.fw : 2 * q.fw, C = is_feat ? kFeatC : kSkipC;
+                    const float *base = (is_feat ? F + kb * 64 : S) + l16 * 4;
+#pragma unroll 4
+                    for (int it = 0; it < 16; ++it) {
+                        const int src = it * 2 + half, r = g * 32 + src;
+                        const float nx = __shfl_sync(0xffffffffu, my_nx, src), ny = __shfl_sync(0xffffffffu, my_ny, src);
+                        const TapsTc t = make_taps_tc(nx, ny, H, W);
+                        float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (t.valid & (1u << k)) {
+                                const float4 v = __ldg(reinterpret_cast<const float4 *>(base + ((size_t)(t.y0 + (k >> 1)) * W + (t.x0 + (k & 1))) * C));
+                                v0 = fmaf(v.x, t.w[k], v0); v1 = fmaf(v.y, t.w[k], v1);
+                                v2 = fmaf(v.z, t.w[k], v2); v3 = fmaf(v.w, t.w[k], v3);
+                            }
+                        }
+                        uint32_t h01, l01, h23, l23;
+                        split2(v0, v1, h01, l01);
+                        split2(v2, v3, h23, l23);
+                        const uint32_t off = sw128(r, l16 >> 1) + (l16 & 1) * 8;
+                        *reinterpret_cast<uint2 *>(hi + off) = make_uint2(h01, h23);
+                        *reinterpret_cast<uint2 *>(lo + off) = make_uint2(l01, l23);
+                    }
+                } else {
+                    // z_feat = [x, y, z - 2.2] (model/chore.py:128-129) + 13 zero channels: one k-step, lane = row
+                    const int r = g * 32 + lane;
+                    uint32_t h01, l01, h23, l23;
+                    split2(my_x, my_y, h01, l01);
+                    split2(__fsub_rn(my_z, 2.2f), 0.f, h23, l23);
+                    *reinterpret_cast<uint4 *>(hi + sw128(r, 0)) = make_uint4(h01, h23, 0u, 0u);
+                    *reinterpret_cast<uint4 *>(lo + sw128(r, 0)) = make_uint4(l01, l23, 0u, 0u);
+                    *reinterpret_cast<uint4 *>(hi + sw128(r, 1)) = make_uint4(0u, 0u, 0u, 0u);
+                    *reinterpret_cast<uint4 *>(lo + sw128(r, 1)) = make_uint4(0u, 0u, 0u, 0u);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bars->a_full[sa]);
+            }
+        }
+    } else {
+        // =============================== epilogue warps ===============================
+        const int e = warp - kEpiWarp0;              // 0..7
+        const int quarter = warp & 3;                // TMEM lane quarter this warp may access
+        const int colhalf = e >> 2;                  // 0: columns 0-63, 1: columns 64-127
+        const int row = quarter * 32 + lane;         // point of the tile owned by this thread
+        uint32_t actblk = 0;                         // activation block counter (this warp's column half adds colhalf)
+        uint32_t tile_i = 0;
+        for (long long tile = first_tile; tile < q.total_tiles; tile += tile_stride, ++tile_i) {
+            const int b = q.grid_mode ? q.batch_index : (int)(tile / q.tiles_per_b);
+            const long long n = (tile % q.tiles_per_b) * kTileM + row;
+            const bool live = n < q.n_count;
+            bool inimg = false;
+            {
+                float x = 0.f, y = 0.f, z = 1.f, nx, ny;
+                if (live) load_point(q, b, n, x, y, z);
+                project_tc(x, y, z, __ldg(q.crop_center + b * 2), __ldg(q.crop_center + b * 2 + 1), nx, ny);
+                inimg = (nx >= -1.0f) && (nx <= 1.0f) && (ny >= -1.0f) && (ny <= 1.0f);
+                if (q.in_img && live && e < 4) q.in_img[(size_t)b * q.N + q.n_start + n] = inimg;
+            }
+            for (int layer = 0; layer < 3; ++layer) {
+                for (int h = 0; h < 4; ++h) {
+                    if (layer == 2 && (h & 1) != colhalf) continue;      // layer 3: heads are split between the groups
+                    mbar_wait(&bars->tm_full[h], (tile_i * 3 + layer) & 1);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + h * 128 + colhalf * 64;
+                    const float *bias = (layer == 0 ? q.b1 : (layer == 1 ? q.b2 : q.b3)) + h * 128 + colhalf * 64;
+                    if (layer < 2) {
+                        // bias + ReLU + hi/lo split -> activation k-block `colhalf` of head h
+                        const uint32_t blk = actblk + colhalf;
+                        const int sa = blk % kNACT;
+                        mbar_wait(&bars->act_empty[sa], ((blk / kNACT) & 1) ^ 1);
+                        uint8_t *hi = ringAct + (size_t)sa * kStageA, *lo = hi + kPanelBytes;
+#pragma unroll
+                        for (int part = 0; part < 2; ++part) {
+                            uint32_t v[32];
+                            tmem_ld32(taddr + part * 32, v);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int c8 = 0; c8 < 4; ++c8) {     // 8 columns = one 16-byte chunk of fp16
+                                uint32_t hh[4], ll[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const int c = c8 * 8 + j * 2;
+                                    const float a0 = fmaxf(__uint_as_float(v[c]) + __ldg(bias + part * 32 + c), 0.f);
+                                    const float a1 = fmaxf(__uint_as_float(v[c + 1]) + __ldg(bias + part * 32 + c + 1), 0.f);
+                                    split2(a0, a1, hh[j], ll[j]);
+                                }
+                                const uint32_t off = sw128(row, part * 4 + c8);
+                                *reinterpret_cast<uint4 *>(hi + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+                                *reinterpret_cast<uint4 *>(lo + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+                            }
+                        }
+                        tc_fence_before();
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bars->act_full[sa]);
+                        actblk += 2;
+                    } else {
+                        // layer 3: ReLU, then the last (<= 14-wide) layer in fp32 on the CUDA cores.  Here the
+                        // two warp groups split the HEADS (group 0: df, parts; group 1: pca, centers) and each
+                        // thread walks all 128 columns of its row, so no partial sums have to be exchanged.
+                        const int nout = head_out_tc(h);
+                        const uint32_t taddr3 = tmem_base + ((uint32_t)(quarter * 32) << 16) + h * 128;
+                        const float *bias3 = q.b3 + h * 128;
+                        float acc[14];
+#pragma unroll
+                        for (int o = 0; o < 14; ++o) acc[o] = 0.f;
+#pragma unroll 1
+                        for (int part = 0; part < 4; ++part) {
+                            uint32_t v[32];
+                            tmem_ld32(taddr3 + part * 32, v);
+                            tmem_ld_wait();
+                            float a[32];
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) a[c] = fmaxf(__uint_as_float(v[c]) + __ldg(bias3 + part * 32 + c), 0.f);
+                            const float *w4 = q.w4 + ((size_t)h * 16) * kHidden + part * 32;
+#pragma unroll
+                            for (int o = 0; o < 14; ++o) {
+                                if (o < nout) {
+                                    float s = acc[o];
+#pragma unroll
+                                    for (int c4 = 0; c4 < 8; ++c4) {
+                                        const float4 w = __ldg(reinterpret_cast<const float4 *>(w4 + (size_t)o * kHidden) + c4);
+                                        s = fmaf(a[c4 * 4], w.x, s); s = fmaf(a[c4 * 4 + 1], w.y, s);
+                                        s = fmaf(a[c4 * 4 + 2], w.z, s); s = fmaf(a[c4 * 4 + 3], w.w, s);
+                                    }
+                                    acc[o] = s;
+                                }
+                            }
+                        }
+                        // the accumulator of head h is drained: the next tile's layer 1 may overwrite it
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bars->tm_empty[h]);
+                        if (((q.head_mask >> h) & 1) && live) {
+                            float *outp = q.out[h];
+#pragma unroll
+                            for (int o = 0; o < 14; ++o) {
+                                if (o < nout) {
+                                    float val = acc[o] + __ldg(q.b4 + h * 16 + o);
+                                    if (h == 0 && !inimg) val = 5.0f;          // model/chore.py:147-150
+                                    outp[((size_t)b * nout + o) * q.N + q.n_start + n] = val;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// fp16 hi/lo panels of W[n][k] (n = output channel, k = input channel of this k-block), 128B-swizzled
+void pack_panel(const float *w /* 128 x 64 row-major (n, k) */, uint8_t *hi, uint8_t *lo) {
+    for (int n = 0; n < 128; ++n)
+        for (int k = 0; k < 64; ++k) {
+            float v = w[n * 64 + k];
+            v = v > 65504.f ? 65504.f : (v < -65504.f ? -65504.f : v);
+            const __half h = __float2half_rn(v);
+            const __half l = __float2half_rn(v - __half2float(h));
+            const size_t off = (size_t)n * 128 + (size_t)(((k >> 3) ^ (n & 7)) << 4) + (size_t)(k & 7) * 2;
+            const unsigned short hs = __half_as_ushort(h), ls = __half_as_ushort(l);
+            memcpy(hi + off, &hs, 2);
+            memcpy(lo + off, &ls, 2);
+        }
+}
+
+}   // namespace
+
+// builds the per-tile weight stream from the fp32 MLP weights already held by the handle
+int query_tc_pack_weights(chore_handle *h, const std::vector<float> &w1 /*[4][128][323]*/,
+                          const std::vector<float> &w2 /*[4][128][128]*/, const std::vector<float> &w3) {
+    std::vector<uint8_t> stream((size_t)kUnitsPerTile * kPanelBytes, 0);
+    std::vector<float> tmp(128 * 64);
+    size_t u = 0;
+    for (int kb = 0; kb < kL1Blocks; ++kb)
+        for (int hd = 0; hd < 4; ++hd) {
+            for (int n = 0; n < 128; ++n)
+                for (int k = 0; k < 64; ++k) {
+                    int c = -1;                       // channel of the reference's 323-vector
+                    if (kb < 4) c = kb * 64 + k;      // hourglass feature
+                    else if (kb == 4) c = 259 + k;    // stem skip feature
+                    else if (k < 3) c = 256 + k;      // x, y, z - 2.2
+                    tmp[n * 64 + k] = c >= 0 ? w1[((size_t)hd * 128 + n) * kPointC + c] : 0.f;
+                }
+            pack_panel(tmp.data(), stream.data() + u * kPanelBytes, stream.data() + (u + 1) * kPanelBytes);
+            u += 2;
+        }
+    for (int layer = 0; layer < 2; ++layer) {
+        const std::vector<float> &w = layer == 0 ? w2 : w3;
+        for (int hd = 0; hd < 4; ++hd)
+            for (int kb = 0; kb < 2; ++kb) {
+                for (int n = 0; n < 128; ++n)
+                    for (int k = 0; k < 64; ++k) tmp[n * 64 + k] = w[((size_t)hd * 128 + n) * 128 + kb * 64 + k];
+                pack_panel(tmp.data(), stream.data() + u * kPanelBytes, stream.data() + (u + 1) * kPanelBytes);
+                u += 2;
+            }
+    }
+    if (u != (size_t)kUnitsPerTile) {
+        chore_set_error("internal: weight stream has %zu panels, expected %d", u, kUnitsPerTile);
+        return CHORE_ERR_INVALID;
+    }
+    if (int rc = chore_dev_alloc(h, reinterpret_cast<void **>(&h->mlp.wstream), stream.size())) return rc;
+    CHORE_CUDA(cudaMemcpy(h->mlp.wstream, stream.data(), stream.size(), cudaMemcpyHostToDevice));
+    return CHORE_OK;
+}
+
+int query_tc_launch(chore_handle *h, const float *feat, const float *skip, int fh, int fw, const float *points,
+                    const float *crop_center, int B, long long N, long long n_start, long long n_count, int grid_mode,
+                    int batch_index, const int *res, const double *step, const double *bmin, unsigned head_mask,
+                    float *const outs[4], unsigned char *in_img, cudaStream_t st) {
+    TcParams q{};
+    q.feat = feat; q.skip = skip; q.fh = fh; q.fw = fw;
+    q.points = points; q.crop_center = crop_center;
+    q.B = B; q.N = N; q.n_start = n_start; q.n_count = n_count;
+    q.grid_mode = grid_mode; q.batch_index = batch_index;
+    if (grid_mode) {
+        q.ry = res[1]; q.rz = res[2];
+        for (int i = 0; i < 3; ++i) { q.step[i] = step[i]; q.bmin[i] = bmin[i]; }
+    }
+    q.head_mask = head_mask;
+    for (int i = 0; i < 4; ++i) q.out[i] = outs[i];
+    q.in_img = in_img;
+    const MlpWeights &m = h->mlp;
+    q.wstream = m.wstream; q.b1 = m.b1; q.b2 = m.b2; q.b3 = m.b3; q.w4 = m.w4; q.b4 = m.b4;
+    q.tiles_per_b = (n_count + kTileM - 1) / kTileM;
+    q.total_tiles = q.tiles_per_b * (grid_mode ? 1 : B);
+    static bool configured = false;
+    if (!configured) {
+        CHORE_CUDA(cudaFuncSetAttribute(query_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        configured = true;
+    }
+    const long long grid = q.total_tiles < h->sm_count ? q.total_tiles : h->sm_count;
+    CHORE_LAUNCH(query_tc_kernel, (unsigned)grid, kThreads, kSmemBytes, st, q);
+    return CHORE_OK;
+}

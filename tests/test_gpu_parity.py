@@ -195,7 +195,7 @@ def test_approx_surface_vs_golden(net, sd):
             got, _ = gen.approx_surface(net, cur.to(DEV).requires_grad_(True), 1, {"crop_center": cc}, name)
             d = (got.detach().cpu() - nxt).abs().amax(-1)
             # a point whose gradient is ~0 has an ill-defined direction: allow a sliver of outliers
-            assert d.median() < 2e-6 and (d < 1e-4).float().mean() > 0.99, (name, step, d.median().item(), (d < 1e-4).float().mean().item())
+            assert d.median() < 1e-5 and (d < 1e-4).float().mean() > 0.99, (name, step, d.median().item(), (d < 1e-4).float().mean().item())
             cur = nxt
     if int(g["seed"]) == 31:        # the teacher-forced chain reproduces the golden end points
         assert (cur - torch.from_numpy(g["samples_object"])).abs().max() < 1e-3
