@@ -116,7 +116,7 @@ int chore_dev_alloc(chore_handle *h, void **p, size_t bytes);
 
 // tensor-core query path (query_tc.cu)
 int query_tc_pack_weights(chore_handle *h, const std::vector<float> &w1, const std::vector<float> &w2,
-                          const std::vector<float> &w3);
+                          const std::vector<float> &w3, const std::vector<float> &w4);
 int query_tc_launch(chore_handle *h, const float *feat, const float *skip, int fh, int fw, const float *points,
                     const float *crop_center, int B, long long N, long long n_start, long long n_count, int grid_mode,
                     int batch_index, const int *res, const double *step, const double *bmin, unsigned head_mask,

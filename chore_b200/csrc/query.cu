@@ -621,7 +621,7 @@ int query_load_weights(chore_handle *h, const std::map<std::string, const chore_
     rc |= upload(h, &m.w3t, w3t); rc |= upload(h, &m.w3o, w3o); rc |= upload(h, &m.b3, b3);
     rc |= upload(h, &m.w4, w4); rc |= upload(h, &m.b4, b4);
     if (rc) return CHORE_ERR_CUDA;
-    if (int rc2 = query_tc_pack_weights(h, raw1, raw2, raw3)) return rc2;
+    if (int rc2 = query_tc_pack_weights(h, raw1, raw2, raw3, w4)) return rc2;
     m.loaded = true;
     return CHORE_OK;
 }

@@ -26,6 +26,8 @@
 #include "common.cuh"
 
 #include <cuda_fp16.h>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace {
@@ -36,7 +38,10 @@ constexpr int kPanelBytes = kTileM * kKB * 2;          // 16 KB: 128 rows x 64 f
 constexpr int kStageA = 2 * kPanelBytes;               // hi + lo
 constexpr int kNA = 2, kNACT = 3, kNW = 4;             // ring depths
 constexpr int kL1Blocks = 6;                 // 4 x feat(64) | skip(64) | xyz(3, one k-step)
-constexpr int kUnitsPerTile = kL1Blocks * 4 * 2 + 2 * (4 * 2 * 2);   // 48 + 32 = 80 weight panels
+constexpr int kBigUnits = kL1Blocks * 4 * 2 + 2 * (4 * 2 * 2);       // 48 + 32 = 80 panels of 16 KB (layers 1-3)
+constexpr int kUnitsPerTile = kBigUnits + 4;                          // + one 8 KB panel per head for the last layer
+constexpr int kSmallPanelBytes = 8192;                                // [kb0 hi | kb0 lo | kb1 hi | kb1 lo] x (16 rows x 128 B)
+constexpr size_t kStreamBytes = (size_t)kBigUnits * kPanelBytes + 4 * (size_t)kSmallPanelBytes;
 constexpr int kThreads = 14 * 32;
 constexpr int kGatherWarp0 = 2, kEpiWarp0 = 6;
 constexpr size_t kSmemBytes = 1024 + (size_t)kNA * kStageA + (size_t)kNACT * kStageA + (size_t)kNW * kPanelBytes + 512;
@@ -62,6 +67,7 @@ struct TcParams {
     const float *b1, *b2, *b3;        // [4][128]
     const float *w4, *b4;             // [4][16][128], [4][16] fp32
     long long tiles_per_b, total_tiles;
+    unsigned long long *dbg;          // optional [grid][16] wait-cycle counters (CHORE_B200_TC_TRACE)
 };
 
 __host__ __device__ __forceinline__ int head_out_tc(int h) { return h == 0 ? 2 : (h == 1 ? 9 : (h == 2 ? 14 : 6)); }
@@ -90,6 +96,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {}
 }
+// wait that also accumulates the cycles spent blocked (tracing builds pass a non-null counter)
+__device__ __forceinline__ void mbar_wait_t(uint64_t *bar, uint32_t parity, unsigned long long *acc) {
+    if (acc == nullptr) { mbar_wait(bar, parity); return; }
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    *acc += (unsigned long long)(clock64() - t0);
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -101,24 +114,25 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 B apart
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);          // start address
-    d |= (uint64_t)1 << 16;                          // leading byte offset (ignored for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset: 8 rows x 128 B
-    d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
-    return d;
-}
+// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 B apart.
+// high word: stride byte offset 1024 >> 4 | version 1 (bit 46) | SWIZZLE_128B = 2 (bits 61-63)
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+// low word: start address >> 4 (14 bits) | leading byte offset field = 1 (ignored for swizzled K-major).
+// Advancing K by one 16-element step (32 B) inside the swizzle atom adds 2 to this word.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
 // instruction descriptor: kind::f16, A = B = F16, D = F32, both K-major, M x N
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
-                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %4, 0;\nmov.b64 da, {%1, %5};\nmov.b64 db, {%2, %5};\n"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n}"
+                 ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -133,6 +147,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
                    "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                  : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // x = hi + lo, both fp16 (clamped to the fp16 range); packs two consecutive values
@@ -143,6 +164,17 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t 
     const __half la = __float2half_rn(a - __half2float(ha)), lb = __float2half_rn(b - __half2float(hb));
     hi = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
     lo = (uint32_t)__half_as_ushort(la) | ((uint32_t)__half_as_ushort(lb) << 16);
+}
+
+// same for non-negative inputs (post-ReLU activations), with packed conversions
+__device__ __forceinline__ void split2_pos(float a, float b, uint32_t &hi, uint32_t &lo) {
+    a = fminf(a, 65504.f);
+    b = fminf(b, 65504.f);
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 back = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - back.x, b - back.y);
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
 }
 
 // byte offset of 16-byte chunk `c` (8 fp16) of row `r` inside a 128B-swizzled K-major panel
@@ -223,6 +255,11 @@ __global__ void __launch_bounds__(kThreads, 1) query_tc_kernel(const TcParams q)
     Bars *bars = reinterpret_cast<Bars *>(ringW + (size_t)kNW * kPanelBytes);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // tracing: one counter row per CTA, written by lane 0 of warps 0, 1, 2 and 6 only
+    unsigned long long dbg_local[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const bool dbg_on = q.dbg != nullptr && lane == 0 && (warp == 0 || warp == 1 || warp == 2 || warp == 6);
+    const long long dbg_t0 = clock64();
+#define DBG(i) (dbg_on ? &dbg_local[i] : nullptr)
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kNA; ++i) { mbar_init(&bars->a_full[i], 4); mbar_init(&bars->a_empty[i], 1); }
@@ -238,107 +275,159 @@ __global__ void __launch_bounds__(kThreads, 1) query_tc_kernel(const TcParams q)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = bars->tmem_base;
+    // warp-uniform by construction (lets the issue loop live in uniform registers)
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, bars->tmem_base, 0);
 
     const long long first_tile = blockIdx.x, tile_stride = gridDim.x;
 
     if (warp == 0) {
         // =============================== weight producer ===============================
-        if (lane == 0) {
-            uint32_t u = 0;   // running panel counter over all tiles
-            for (long long tile = first_tile; tile < q.total_tiles; tile += tile_stride) {
-                for (int i = 0; i < kUnitsPerTile; ++i, ++u) {
-                    const int s = u % kNW;
-                    const uint32_t ph = (u / kNW) & 1;
-                    mbar_wait(&bars->w_empty[s], ph ^ 1);
-                    mbar_arrive_expect_tx(&bars->w_full[s], kPanelBytes);
-                    bulk_g2s(ringW + (size_t)s * kPanelBytes, q.wstream + (size_t)i * kPanelBytes, kPanelBytes, &bars->w_full[s]);
+        // the whole warp walks the loop (uniform control flow); one elected lane issues the copies
+        uint32_t u = 0;   // running panel counter over all tiles
+        for (long long tile = first_tile; tile < q.total_tiles; tile += tile_stride) {
+            for (int i = 0; i < kUnitsPerTile; ++i, ++u) {
+                const int s = u % kNW;
+                mbar_wait_t(&bars->w_empty[s], ((u / kNW) & 1) ^ 1, DBG(0));
+                if (elect_one()) {
+                    const uint32_t bytes = i < kBigUnits ? kPanelBytes : kSmallPanelBytes;
+                    const size_t off = i < kBigUnits ? (size_t)i * kPanelBytes
+                                                     : (size_t)kBigUnits * kPanelBytes + (size_t)(i - kBigUnits) * kSmallPanelBytes;
+                    mbar_arrive_expect_tx(&bars->w_full[s], bytes);
+                    bulk_g2s(ringW + (size_t)s * kPanelBytes, q.wstream + off, bytes, &bars->w_full[s]);
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
         // =============================== MMA issuer ===============================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(kTileM, 128);
-            uint32_t u = 0;        // weight panel counter
-            uint32_t ablk = 0;     // A ring block counter
-            uint32_t actblk = 0;   // activation ring block counter
-            uint32_t tile_i = 0;
-            for (long long tile = first_tile; tile < q.total_tiles; tile += tile_stride, ++tile_i) {
-                // ---- layer 1: 6 k-blocks x 4 heads, all four accumulators live ----
-                for (int kb = 0; kb < kL1Blocks; ++kb, ++ablk) {
-                    const int sa = ablk % kNA;
-                    mbar_wait(&bars->a_full[sa], (ablk / kNA) & 1);
-                    tc_fence_after();
-                    const uint32_t a_hi = smem_u32(ringA + (size_t)sa * kStageA), a_lo = a_hi + kPanelBytes;
-                    const int ksteps = kb == kL1Blocks - 1 ? 1 : 4;     // the xyz block holds 16 channels
-                    for (int h = 0; h < 4; ++h) {
-                        if (kb == 0) {   // accumulator of head h must have been drained (previous tile)
-                            mbar_wait(&bars->tm_empty[h], (tile_i & 1) ^ 1);
-                            tc_fence_after();
-                        }
-                        const uint32_t d = tmem_base + h * 128;
-                        {   // panel w_hi: a_hi*w_hi + a_lo*w_hi
-                            const int s = u % kNW;
-                            mbar_wait(&bars->w_full[s], (u / kNW) & 1);
-                            tc_fence_after();
-                            const uint32_t wb = smem_u32(ringW + (size_t)s * kPanelBytes);
-                            for (int ks = 0; ks < ksteps; ++ks) {
-                                umma_f16(d, make_desc(a_hi + ks * 32), make_desc(wb + ks * 32), idesc, (kb | ks) != 0);
-                                umma_f16(d, make_desc(a_lo + ks * 32), make_desc(wb + ks * 32), idesc, 1);
-                            }
-                            umma_commit(&bars->w_empty[s]);
-                            ++u;
-                        }
-                        {   // panel w_lo: a_hi*w_lo
-                            const int s = u % kNW;
-                            mbar_wait(&bars->w_full[s], (u / kNW) & 1);
-                            tc_fence_after();
-                            const uint32_t wb = smem_u32(ringW + (size_t)s * kPanelBytes);
-                            for (int ks = 0; ks < ksteps; ++ks) umma_f16(d, make_desc(a_hi + ks * 32), make_desc(wb + ks * 32), idesc, 1);
-                            umma_commit(&bars->w_empty[s]);
-                            ++u;
-                        }
-                        if (kb == kL1Blocks - 1) umma_commit(&bars->tm_full[h]);   // layer-1 accumulator of head h complete
-                    }
-                    umma_commit(&bars->a_empty[sa]);
-                }
-                // ---- layers 2 and 3: per head, A operand = activation blocks written by the epilogue ----
-                for (int layer = 0; layer < 2; ++layer) {
-                    for (int h = 0; h < 4; ++h) {
-                        const uint32_t d = tmem_base + h * 128;
-                        // both activation blocks must be complete before the accumulator is overwritten
-                        const uint32_t b0 = actblk, b1 = actblk + 1;
-                        mbar_wait(&bars->act_full[b0 % kNACT], (b0 / kNACT) & 1);
-                        mbar_wait(&bars->act_full[b1 % kNACT], (b1 / kNACT) & 1);
+        // All 32 lanes run the loop converged so that every operand is warp-uniform; only the tcgen05
+        // instructions themselves are predicated on one elected lane.
+        constexpr uint32_t idesc = make_idesc(kTileM, 128), idesc16 = make_idesc(kTileM, 16);
+        const uint32_t ringA_lo = desc_lo(smem_u32(ringA)), ringAct_lo = desc_lo(smem_u32(ringAct)), ringW_lo = desc_lo(smem_u32(ringW));
+        constexpr uint32_t kStageLo = kStageA >> 4, kPanelLo = kPanelBytes >> 4;
+        uint32_t u = 0;        // weight panel counter
+        uint32_t ablk = 0;     // A ring block counter
+        uint32_t actblk = 0;   // activation ring block counter
+        uint32_t tile_i = 0;
+        for (long long tile = first_tile; tile < q.total_tiles; tile += tile_stride, ++tile_i) {
+            // ---- layer 1: 6 k-blocks x 4 heads, all four accumulators live ----
+            for (int kb = 0; kb < kL1Blocks; ++kb, ++ablk) {
+                const int sa = ablk % kNA;
+                mbar_wait_t(&bars->a_full[sa], (ablk / kNA) & 1, DBG(1));
+                tc_fence_after();
+                const uint32_t a_hi = ringA_lo + sa * kStageLo, a_lo = a_hi + kPanelLo;
+                const bool last = kb == kL1Blocks - 1;       // the xyz block holds 16 channels: one k-step
+#pragma unroll 1
+                for (int h = 0; h < 4; ++h) {
+                    if (kb == 0) {   // accumulator of head h must have been drained (previous tile)
+                        mbar_wait_t(&bars->tm_empty[h], (tile_i & 1) ^ 1, DBG(2));
                         tc_fence_after();
+                    }
+                    const uint32_t d = tmem_base + h * 128;
+                    const int s0 = u % kNW, s1 = (u + 1) % kNW;
+                    mbar_wait_t(&bars->w_full[s0], (u / kNW) & 1, DBG(3));       // panel w_hi: a_hi*w_hi + a_lo*w_hi
+                    tc_fence_after();
+                    const uint32_t w0 = ringW_lo + s0 * kPanelLo;
+                    if (elect_one()) {
+                        umma_f16(d, a_hi, w0, idesc, kb != 0);
+                        umma_f16(d, a_lo, w0, idesc, 1);
+                        if (!last) {
+#pragma unroll
+                            for (int ks = 1; ks < 4; ++ks) {
+                                umma_f16(d, a_hi + 2 * ks, w0 + 2 * ks, idesc, 1);
+                                umma_f16(d, a_lo + 2 * ks, w0 + 2 * ks, idesc, 1);
+                            }
+                        }
+                        umma_commit(&bars->w_empty[s0]);
+                    }
+                    __syncwarp();
+                    mbar_wait_t(&bars->w_full[s1], ((u + 1) / kNW) & 1, DBG(3));  // panel w_lo: a_hi*w_lo
+                    tc_fence_after();
+                    const uint32_t w1 = ringW_lo + s1 * kPanelLo;
+                    if (elect_one()) {
+                        umma_f16(d, a_hi, w1, idesc, 1);
+                        if (!last) {
+#pragma unroll
+                            for (int ks = 1; ks < 4; ++ks) umma_f16(d, a_hi + 2 * ks, w1 + 2 * ks, idesc, 1);
+                        }
+                        umma_commit(&bars->w_empty[s1]);
+                        if (last) umma_commit(&bars->tm_full[h]);       // layer-1 accumulator of head h complete
+                        if (h == 3) umma_commit(&bars->a_empty[sa]);
+                    }
+                    __syncwarp();
+                    u += 2;
+                }
+            }
+            // ---- layers 2, 3 (128 wide) and 4 (16 wide): per head, A operand = activation blocks ----
+#pragma unroll 1
+            for (int layer = 1; layer < 4; ++layer) {
+#pragma unroll 1
+                for (int h = 0; h < 4; ++h) {
+                    const uint32_t d = tmem_base + h * 128;
+                    // both activation blocks must be complete before the accumulator is overwritten
+                    const uint32_t b0 = actblk, b1 = actblk + 1;
+                    mbar_wait_t(&bars->act_full[b0 % kNACT], (b0 / kNACT) & 1, DBG(4));
+                    mbar_wait_t(&bars->act_full[b1 % kNACT], (b1 / kNACT) & 1, DBG(4));
+                    tc_fence_after();
+                    if (layer < 3) {
+#pragma unroll 1
                         for (int kb = 0; kb < 2; ++kb, ++actblk) {
                             const int sa = actblk % kNACT;
-                            const uint32_t a_hi = smem_u32(ringAct + (size_t)sa * kStageA), a_lo = a_hi + kPanelBytes;
-                            {
-                                const int s = u % kNW;
-                                mbar_wait(&bars->w_full[s], (u / kNW) & 1);
-                                tc_fence_after();
-                                const uint32_t wb = smem_u32(ringW + (size_t)s * kPanelBytes);
-                                for (int ks = 0; ks < 4; ++ks) {
-                                    umma_f16(d, make_desc(a_hi + ks * 32), make_desc(wb + ks * 32), idesc, (kb | ks) != 0);
-                                    umma_f16(d, make_desc(a_lo + ks * 32), make_desc(wb + ks * 32), idesc, 1);
+                            const uint32_t a_hi = ringAct_lo + sa * kStageLo, a_lo = a_hi + kPanelLo;
+                            const int s0 = u % kNW, s1 = (u + 1) % kNW;
+                            mbar_wait_t(&bars->w_full[s0], (u / kNW) & 1, DBG(5));
+                            tc_fence_after();
+                            const uint32_t w0 = ringW_lo + s0 * kPanelLo;
+                            if (elect_one()) {
+                                umma_f16(d, a_hi, w0, idesc, kb != 0);
+                                umma_f16(d, a_lo, w0, idesc, 1);
+#pragma unroll
+                                for (int ks = 1; ks < 4; ++ks) {
+                                    umma_f16(d, a_hi + 2 * ks, w0 + 2 * ks, idesc, 1);
+                                    umma_f16(d, a_lo + 2 * ks, w0 + 2 * ks, idesc, 1);
                                 }
-                                umma_commit(&bars->w_empty[s]);
-                                ++u;
+                                umma_commit(&bars->w_empty[s0]);
                             }
-                            {
-                                const int s = u % kNW;
-                                mbar_wait(&bars->w_full[s], (u / kNW) & 1);
-                                tc_fence_after();
-                                const uint32_t wb = smem_u32(ringW + (size_t)s * kPanelBytes);
-                                for (int ks = 0; ks < 4; ++ks) umma_f16(d, make_desc(a_hi + ks * 32), make_desc(wb + ks * 32), idesc, 1);
-                                umma_commit(&bars->w_empty[s]);
-                                ++u;
+                            __syncwarp();
+                            mbar_wait_t(&bars->w_full[s1], ((u + 1) / kNW) & 1, DBG(5));
+                            tc_fence_after();
+                            const uint32_t w1 = ringW_lo + s1 * kPanelLo;
+                            if (elect_one()) {
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) umma_f16(d, a_hi + 2 * ks, w1 + 2 * ks, idesc, 1);
+                                umma_commit(&bars->w_empty[s1]);
+                                umma_commit(&bars->act_empty[sa]);
+                                if (kb == 1) umma_commit(&bars->tm_full[h]);
                             }
-                            umma_commit(&bars->act_empty[sa]);
+                            __syncwarp();
+                            u += 2;
                         }
-                        umma_commit(&bars->tm_full[h]);
+                    } else {
+                        // last layer (<= 14 outputs, padded to N = 16): one 8 KB panel [kb0 hi | kb0 lo | kb1 hi | kb1 lo]
+                        const int s0 = u % kNW;
+                        mbar_wait_t(&bars->w_full[s0], (u / kNW) & 1, DBG(5));
+                        tc_fence_after();
+                        const uint32_t w = ringW_lo + s0 * kPanelLo;
+                        const int sa0 = actblk % kNACT, sa1 = (actblk + 1) % kNACT;
+                        if (elect_one()) {
+#pragma unroll
+                            for (int kb = 0; kb < 2; ++kb) {
+                                const uint32_t a_hi = ringAct_lo + (kb == 0 ? sa0 : sa1) * kStageLo, a_lo = a_hi + kPanelLo;
+                                const uint32_t w_hi = w + kb * (4096 >> 4), w_lo = w_hi + (2048 >> 4);
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) {
+                                    umma_f16(d, a_hi + 2 * ks, w_hi + 2 * ks, idesc16, (kb | ks) != 0);
+                                    umma_f16(d, a_lo + 2 * ks, w_hi + 2 * ks, idesc16, 1);
+                                    umma_f16(d, a_hi + 2 * ks, w_lo + 2 * ks, idesc16, 1);
+                                }
+                                umma_commit(&bars->act_empty[kb == 0 ? sa0 : sa1]);
+                            }
+                            umma_commit(&bars->w_empty[s0]);
+                            umma_commit(&bars->tm_full[h]);
+                        }
+                        __syncwarp();
+                        u += 1;
+                        actblk += 2;
                     }
                 }
             }
@@ -361,7 +450,7 @@ __global__ void __launch_bounds__(kThreads, 1) query_tc_kernel(const TcParams q)
             project_tc(my_x, my_y, my_z, ccx, ccy, my_nx, my_ny);
             for (int kb = 0; kb < kL1Blocks; ++kb, ++ablk) {
                 const int sa = ablk % kNA;
-                mbar_wait(&bars->a_empty[sa], ((ablk / kNA) & 1) ^ 1);
+                mbar_wait_t(&bars->a_empty[sa], ((ablk / kNA) & 1) ^ 1, DBG(6));
                 uint8_t *hi = ringA + (size_t)sa * kStageA, *lo = hi + kPanelBytes;
                 if (kb < 5) {
                     const bool is_feat = kb < 4;
@@ -411,8 +500,7 @@ __global__ void __launch_bounds__(kThreads, 1) query_tc_kernel(const TcParams q)
         const int colhalf = e >> 2;                  // 0: columns 0-63, 1: columns 64-127
         const int row = quarter * 32 + lane;         // point of the tile owned by this thread
         uint32_t actblk = 0;                         // activation block counter (this warp's column half adds colhalf)
-        uint32_t tile_i = 0;
-        for (long long tile = first_tile; tile < q.total_tiles; tile += tile_stride, ++tile_i) {
+        for (long long tile = first_tile; tile < q.total_tiles; tile += tile_stride) {
             const int b = q.grid_mode ? q.batch_index : (int)(tile / q.tiles_per_b);
             const long long n = (tile % q.tiles_per_b) * kTileM + row;
             const bool live = n < q.n_count;
@@ -424,18 +512,20 @@ __global__ void __launch_bounds__(kThreads, 1) query_tc_kernel(const TcParams q)
                 inimg = (nx >= -1.0f) && (nx <= 1.0f) && (ny >= -1.0f) && (ny <= 1.0f);
                 if (q.in_img && live && e < 4) q.in_img[(size_t)b * q.N + q.n_start + n] = inimg;
             }
-            for (int layer = 0; layer < 3; ++layer) {
+#pragma unroll 1
+            for (int layer = 0; layer < 4; ++layer) {
+#pragma unroll 1
                 for (int h = 0; h < 4; ++h) {
-                    if (layer == 2 && (h & 1) != colhalf) continue;      // layer 3: heads are split between the groups
-                    mbar_wait(&bars->tm_full[h], (tile_i * 3 + layer) & 1);
+                    if (layer == 3 && (h & 1) != colhalf) continue;      // last layer: the heads are split between the groups
+                    mbar_wait_t(&bars->tm_full[h], layer & 1, DBG(7));   // 4 completions per tile: parity = layer & 1
                     tc_fence_after();
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + h * 128 + colhalf * 64;
-                    const float *bias = (layer == 0 ? q.b1 : (layer == 1 ? q.b2 : q.b3)) + h * 128 + colhalf * 64;
-                    if (layer < 2) {
+                    if (layer < 3) {
                         // bias + ReLU + hi/lo split -> activation k-block `colhalf` of head h
+                        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + h * 128 + colhalf * 64;
+                        const float *bias = (layer == 0 ? q.b1 : (layer == 1 ? q.b2 : q.b3)) + h * 128 + colhalf * 64;
                         const uint32_t blk = actblk + colhalf;
                         const int sa = blk % kNACT;
-                        mbar_wait(&bars->act_empty[sa], ((blk / kNACT) & 1) ^ 1);
+                        mbar_wait_t(&bars->act_empty[sa], ((blk / kNACT) & 1) ^ 1, DBG(8));
                         uint8_t *hi = ringAct + (size_t)sa * kStageA, *lo = hi + kPanelBytes;
 #pragma unroll
                         for (int part = 0; part < 2; ++part) {
@@ -448,9 +538,10 @@ __global__ void __launch_bounds__(kThreads, 1) query_tc_kernel(const TcParams q)
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
                                     const int c = c8 * 8 + j * 2;
-                                    const float a0 = fmaxf(__uint_as_float(v[c]) + __ldg(bias + part * 32 + c), 0.f);
-                                    const float a1 = fmaxf(__uint_as_float(v[c + 1]) + __ldg(bias + part * 32 + c + 1), 0.f);
-                                    split2(a0, a1, hh[j], ll[j]);
+                                    const float2 bb = __ldg(reinterpret_cast<const float2 *>(bias + part * 32 + c));
+                                    const float a0 = fmaxf(__uint_as_float(v[c]) + bb.x, 0.f);
+                                    const float a1 = fmaxf(__uint_as_float(v[c + 1]) + bb.y, 0.f);
+                                    split2_pos(a0, a1, hh[j], ll[j]);
                                 }
                                 const uint32_t off = sw128(row, part * 4 + c8);
                                 *reinterpret_cast<uint4 *>(hi + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
@@ -463,50 +554,22 @@ __global__ void __launch_bounds__(kThreads, 1) query_tc_kernel(const TcParams q)
                         if (lane == 0) mbar_arrive(&bars->act_full[sa]);
                         actblk += 2;
                     } else {
-                        // layer 3: ReLU, then the last (<= 14-wide) layer in fp32 on the CUDA cores.  Here the
-                        // two warp groups split the HEADS (group 0: df, parts; group 1: pca, centers) and each
-                        // thread walks all 128 columns of its row, so no partial sums have to be exchanged.
+                        // last layer: 16 accumulator columns -> + bias -> OUT_DIST mask -> HBM (reference layout)
                         const int nout = head_out_tc(h);
-                        const uint32_t taddr3 = tmem_base + ((uint32_t)(quarter * 32) << 16) + h * 128;
-                        const float *bias3 = q.b3 + h * 128;
-                        float acc[14];
-#pragma unroll
-                        for (int o = 0; o < 14; ++o) acc[o] = 0.f;
-#pragma unroll 1
-                        for (int part = 0; part < 4; ++part) {
-                            uint32_t v[32];
-                            tmem_ld32(taddr3 + part * 32, v);
-                            tmem_ld_wait();
-                            float a[32];
-#pragma unroll
-                            for (int c = 0; c < 32; ++c) a[c] = fmaxf(__uint_as_float(v[c]) + __ldg(bias3 + part * 32 + c), 0.f);
-                            const float *w4 = q.w4 + ((size_t)h * 16) * kHidden + part * 32;
-#pragma unroll
-                            for (int o = 0; o < 14; ++o) {
-                                if (o < nout) {
-                                    float s = acc[o];
-#pragma unroll
-                                    for (int c4 = 0; c4 < 8; ++c4) {
-                                        const float4 w = __ldg(reinterpret_cast<const float4 *>(w4 + (size_t)o * kHidden) + c4);
-                                        s = fmaf(a[c4 * 4], w.x, s); s = fmaf(a[c4 * 4 + 1], w.y, s);
-                                        s = fmaf(a[c4 * 4 + 2], w.z, s); s = fmaf(a[c4 * 4 + 3], w.w, s);
-                                    }
-                                    acc[o] = s;
-                                }
-                            }
-                        }
-                        // the accumulator of head h is drained: the next tile's layer 1 may overwrite it
+                        uint32_t v[16];
+                        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + h * 128, v);
+                        tmem_ld_wait();
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&bars->tm_empty[h]);
+                        if (lane == 0) mbar_arrive(&bars->tm_empty[h]);   // the next tile's layer 1 may overwrite head h
                         if (((q.head_mask >> h) & 1) && live) {
-                            float *outp = q.out[h];
+                            float *outp = q.out[h] + ((size_t)b * nout) * q.N + q.n_start + n;
 #pragma unroll
                             for (int o = 0; o < 14; ++o) {
                                 if (o < nout) {
-                                    float val = acc[o] + __ldg(q.b4 + h * 16 + o);
+                                    float val = __uint_as_float(v[o]) + __ldg(q.b4 + h * 16 + o);
                                     if (h == 0 && !inimg) val = 5.0f;          // model/chore.py:147-150
-                                    outp[((size_t)b * nout + o) * q.N + q.n_start + n] = val;
+                                    outp[(size_t)o * q.N] = val;
                                 }
                             }
                         }
@@ -516,6 +579,12 @@ __global__ void __launch_bounds__(kThreads, 1) query_tc_kernel(const TcParams q)
         }
     }
 
+    if (dbg_on) {
+        dbg_local[9] = (unsigned long long)(clock64() - dbg_t0);
+        for (int i = 0; i < 10; ++i)
+            if (dbg_local[i] && (i != 9 || warp == 1)) q.dbg[(size_t)blockIdx.x * 16 + i] = dbg_local[i];
+    }
+#undef DBG
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -525,8 +594,8 @@ __global__ void __launch_bounds__(kThreads, 1) query_tc_kernel(const TcParams q)
 }
 
 // fp16 hi/lo panels of W[n][k] (n = output channel, k = input channel of this k-block), 128B-swizzled
-void pack_panel(const float *w /* 128 x 64 row-major (n, k) */, uint8_t *hi, uint8_t *lo) {
-    for (int n = 0; n < 128; ++n)
+void pack_panel(const float *w /* rows x 64 row-major (n, k) */, int rows, uint8_t *hi, uint8_t *lo) {
+    for (int n = 0; n < rows; ++n)
         for (int k = 0; k < 64; ++k) {
             float v = w[n * 64 + k];
             v = v > 65504.f ? 65504.f : (v < -65504.f ? -65504.f : v);
@@ -541,10 +610,11 @@ void pack_panel(const float *w /* 128 x 64 row-major (n, k) */, uint8_t *hi, uin
 
 }   // namespace
 
-// builds the per-tile weight stream from the fp32 MLP weights already held by the handle
+// builds the per-tile weight stream from the fp32 MLP weights
 int query_tc_pack_weights(chore_handle *h, const std::vector<float> &w1 /*[4][128][323]*/,
-                          const std::vector<float> &w2 /*[4][128][128]*/, const std::vector<float> &w3) {
-    std::vector<uint8_t> stream((size_t)kUnitsPerTile * kPanelBytes, 0);
+                          const std::vector<float> &w2 /*[4][128][128]*/, const std::vector<float> &w3,
+                          const std::vector<float> &w4 /*[4][16][128], rows >= n_out zero*/) {
+    std::vector<uint8_t> stream(kStreamBytes, 0);
     std::vector<float> tmp(128 * 64);
     size_t u = 0;
     for (int kb = 0; kb < kL1Blocks; ++kb)
@@ -557,7 +627,7 @@ int query_tc_pack_weights(chore_handle *h, const std::vector<float> &w1 /*[4][12
                     else if (k < 3) c = 256 + k;      // x, y, z - 2.2
                     tmp[n * 64 + k] = c >= 0 ? w1[((size_t)hd * 128 + n) * kPointC + c] : 0.f;
                 }
-            pack_panel(tmp.data(), stream.data() + u * kPanelBytes, stream.data() + (u + 1) * kPanelBytes);
+            pack_panel(tmp.data(), 128, stream.data() + u * kPanelBytes, stream.data() + (u + 1) * kPanelBytes);
             u += 2;
         }
     for (int layer = 0; layer < 2; ++layer) {
@@ -566,13 +636,21 @@ int query_tc_pack_weights(chore_handle *h, const std::vector<float> &w1 /*[4][12
             for (int kb = 0; kb < 2; ++kb) {
                 for (int n = 0; n < 128; ++n)
                     for (int k = 0; k < 64; ++k) tmp[n * 64 + k] = w[((size_t)hd * 128 + n) * 128 + kb * 64 + k];
-                pack_panel(tmp.data(), stream.data() + u * kPanelBytes, stream.data() + (u + 1) * kPanelBytes);
+                pack_panel(tmp.data(), 128, stream.data() + u * kPanelBytes, stream.data() + (u + 1) * kPanelBytes);
                 u += 2;
             }
     }
-    if (u != (size_t)kUnitsPerTile) {
-        chore_set_error("internal: weight stream has %zu panels, expected %d", u, kUnitsPerTile);
+    if (u != (size_t)kBigUnits) {
+        chore_set_error("internal: weight stream has %zu panels, expected %d", u, kBigUnits);
         return CHORE_ERR_INVALID;
+    }
+    for (int hd = 0; hd < 4; ++hd) {   // last layer: [kb0 hi | kb0 lo | kb1 hi | kb1 lo], 16 rows x 128 B each
+        uint8_t *base = stream.data() + (size_t)kBigUnits * kPanelBytes + (size_t)hd * kSmallPanelBytes;
+        for (int kb = 0; kb < 2; ++kb) {
+            for (int n = 0; n < 16; ++n)
+                for (int k = 0; k < 64; ++k) tmp[n * 64 + k] = w4[((size_t)hd * 16 + n) * 128 + kb * 64 + k];
+            pack_panel(tmp.data(), 16, base + kb * 4096, base + kb * 4096 + 2048);
+        }
     }
     if (int rc = chore_dev_alloc(h, reinterpret_cast<void **>(&h->mlp.wstream), stream.size())) return rc;
     CHORE_CUDA(cudaMemcpy(h->mlp.wstream, stream.data(), stream.size(), cudaMemcpyHostToDevice));
@@ -605,6 +683,28 @@ int query_tc_launch(chore_handle *h, const float *feat, const float *skip, int f
         configured = true;
     }
     const long long grid = q.total_tiles < h->sm_count ? q.total_tiles : h->sm_count;
+    static const bool trace = getenv("CHORE_B200_TC_TRACE") != nullptr;
+    unsigned long long *dbg = nullptr;
+    if (trace) {
+        CHORE_CUDA(cudaMalloc(&dbg, (size_t)grid * 16 * sizeof(unsigned long long)));
+        CHORE_CUDA(cudaMemsetAsync(dbg, 0, (size_t)grid * 16 * sizeof(unsigned long long), st));
+        q.dbg = dbg;
+    }
     CHORE_LAUNCH(query_tc_kernel, (unsigned)grid, kThreads, kSmemBytes, st, q);
+    if (trace) {   // debugging aid: synchronous, prints the mean wait cycles per role
+        std::vector<unsigned long long> hbuf((size_t)grid * 16);
+        CHORE_CUDA(cudaMemcpyAsync(hbuf.data(), dbg, hbuf.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CHORE_CUDA(cudaStreamSynchronize(st));
+        CHORE_CUDA(cudaFree(dbg));
+        static const char *names[10] = {"producer:w_empty", "mma:a_full", "mma:tm_empty", "mma:w_full(L1)", "mma:act_full",
+                                        "mma:w_full(L2/3)", "gather:a_empty", "epi:tm_full", "epi:act_empty", "total"};
+        double sum[10] = {0};
+        for (long long c = 0; c < grid; ++c)
+            for (int i = 0; i < 10; ++i) sum[i] += (double)hbuf[(size_t)c * 16 + i];
+        const double tiles = (double)q.total_tiles / (double)grid;
+        fprintf(stderr, "[tc-trace] tiles/CTA %.1f; cycles per tile:", tiles);
+        for (int i = 0; i < 10; ++i) fprintf(stderr, " %s=%.0f", names[i], sum[i] / (double)grid / tiles);
+        fprintf(stderr, "\n");
+    }
     return CHORE_OK;
 }
