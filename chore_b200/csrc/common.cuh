@@ -65,6 +65,7 @@ struct MlpWeights {
 
 // ---- encoder weights ------------------------------------------------------------------------------
 struct ConvW {
+    unsigned char *wtc = nullptr;   // tensor-core path: [tap][kb][hi|lo] fp16 panels (conv_tc.cu)
     float *w = nullptr;     // [kh][kw][cin][cout]  (HWIO)
     float *bias = nullptr;  // [cout] or null
     int kh = 0, kw = 0, cin = 0, cout = 0;
@@ -122,6 +123,22 @@ int query_tc_launch(chore_handle *h, const float *feat, const float *skip, int f
                     int batch_index, const int *res, const double *step, const double *bmin, unsigned head_mask,
                     float *const outs[4], unsigned char *in_img, cudaStream_t st);
 bool query_use_tensor_cores();   // CHORE_B200_QUERY=simt selects the fp32 SIMT kernel
+
+// tensor-core encoder convolutions (conv_tc.cu)
+struct ConvTcArgs {
+    const float *in; int ld_in, off_in, Cin;
+    int B, H, W, KS, Cout;
+    const unsigned char *wstream;
+    const float *bias;
+    const double *gn_sums; const float *gamma, *beta;   // GroupNorm+ReLU prologue (null = identity)
+    float *out; int ld_out, off_out;
+    const float *res; int ld_res, off_res;
+    float *raw; int ld_raw, off_raw;
+    void *planes;                                       // scratch: 2 * B*H*W*Cp halves (Cp = Cin rounded up to 64)
+};
+bool encoder_use_tensor_cores();   // CHORE_B200_ENCODER=simt selects the fp32 SIMT convolutions
+int conv_tc_pack_weights(chore_handle *h, const float *w, int cout, int cin, int kh, int kw, unsigned char **dev);
+int conv_tc_launch(const ConvTcArgs &a, cudaStream_t st);
 
 // implemented per translation unit
 int query_load_weights(chore_handle *h, const std::map<std::string, const chore_tensor_desc *> &t);

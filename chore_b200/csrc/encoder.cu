@@ -452,8 +452,8 @@ struct Ctx {
 double *gn_stats(Ctx &c, const float *in, int ld, int off, int C, int H, int W) {
     double *slot = c.gn_slot();
     const int HW = H * W;
-    int ctas = (HW + 255) / 256;            // >= 256 pixels per CTA
-    if (ctas > 128) ctas = 128;
+    int ctas = (HW + 63) / 64;              // >= 64 pixels per CTA: enough CTAs to cover 148 SMs at 128^2
+    if (ctas > 1184) ctas = 1184;
     const int ppc = (HW + ctas - 1) / ctas;
     dim3 grid((HW + ppc - 1) / ppc, c.B);
     if ((C / kGroups) % 4 == 0)
@@ -480,6 +480,25 @@ void launch_conv(Ctx &c, const ConvArgs &a) {
 void conv(Ctx &c, const ConvW &w, const ConvArgs &a0) {
     ConvArgs a = a0;
     a.w = w.w; a.bias = w.bias; a.Cin = w.cin; a.Cout = w.cout; a.B = c.B;
+    if (encoder_use_tensor_cores() && w.wtc && a.H >= 8 && a.W >= 8 && w.cout % 32 == 0 && w.cout <= 256) {
+        const size_t mark = c.top;
+        const int cp = (w.cin + 63) / 64 * 64;
+        float *planes = c.alloc((size_t)c.B * a.H * a.W * cp);      // 2 fp16 planes = 4 bytes per element
+        if (!c.dry && c.rc == 0) {
+            ConvTcArgs t{};
+            t.in = a.in; t.ld_in = a.ld_in; t.off_in = a.off_in; t.Cin = w.cin;
+            t.B = c.B; t.H = a.H; t.W = a.W; t.KS = w.kh; t.Cout = w.cout;
+            t.wstream = w.wtc; t.bias = w.bias;
+            t.gn_sums = a.gn_sums; t.gamma = a.gamma; t.beta = a.beta;
+            t.out = a.out; t.ld_out = a.ld_out; t.off_out = a.off_out;
+            t.res = a.res; t.ld_res = a.ld_res; t.off_res = a.off_res;
+            t.raw = a.raw; t.ld_raw = a.ld_raw; t.off_raw = a.off_raw;
+            t.planes = planes;
+            c.rc = conv_tc_launch(t, c.st);
+        }
+        c.top = mark;
+        return;
+    }
     const bool narrow = (w.cout % 64) != 0;
     if (w.kh == 3) {
         if (narrow) launch_conv<3, 32>(c, a); else launch_conv<3, 64>(c, a);
@@ -686,6 +705,8 @@ int encoder_load_weights(chore_handle *h, const std::map<std::string, const chor
             CHORE_CUDA(cudaMemcpy(dev, dst.data(), n * sizeof(float), cudaMemcpyHostToDevice));
             ConvW &w = e.conv[base];
             w.w = dev; w.kh = kh; w.kw = kw; w.cin = ci; w.cout = co;
+            if (base != "image_filter.conv1" && (kh == 1 || kh == 3) && co % 32 == 0 && co <= 256)
+                if (int rc = conv_tc_pack_weights(h, src.data(), co, ci, kh, kw, &w.wtc)) return rc;
         } else if (d->ndim == 1) {
             if (int rc = chore_dev_alloc(h, reinterpret_cast<void **>(&dev), n * sizeof(float))) return rc;
             CHORE_CUDA(cudaMemcpy(dev, src.data(), n * sizeof(float), cudaMemcpyHostToDevice));
