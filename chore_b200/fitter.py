@@ -49,6 +49,54 @@ class _So3Fn(torch.autograd.Function):
         return ctx.handle.project_so3_bwd(m, g_out), None
 
 
+class GraphedStep:
+    """One optimisation step (zero_grad -> losses -> backward -> optimizer.step) captured in a CUDA graph
+    and replayed: no Python, no autograd bookkeeping and no launch gaps on the hot loop.  This is the
+    B200-side replacement for the per-step Python of optimize_smpl / optimize_smpl_object
+    (recon/recon_fit_behave.py:90-163,224-291), which additionally syncs the device every step for its
+    tqdm strings (.item(), :154-157).
+
+    `step_fn()` must run the whole step on the current stream with static tensors (use
+    `torch.optim.Adam(..., capturable=True)` and device-side RNG) and return the loss tensor(s); the
+    returned tensors are refreshed in place by every `__call__`."""
+
+    def __init__(self, step_fn: Callable, warmup: int = 3):
+        self.step_fn = step_fn
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):          # lazy allocations / attribute setup happen outside the capture
+                step_fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        inner = None
+        try:
+            with torch.cuda.graph(self.graph):
+                try:
+                    self.out = step_fn()
+                except Exception as e:      # capture_end() would otherwise mask the real error
+                    inner = e
+        except Exception as outer:
+            raise (inner or outer)
+        if inner is not None:
+            raise inner
+
+    def __call__(self):
+        self.graph.replay()
+        return self.out
+
+
+def backward_to(loss: torch.Tensor, params) -> None:
+    """`loss.backward()` for a captured step: gradients are taken with torch.autograd.grad and stored in
+    `.grad`, so no AccumulateGrad node runs.  Those nodes are bound to the stream on which a parameter was
+    first used (often the legacy default stream), and syncing with that stream is illegal while capturing."""
+    params = list(params)
+    grads = torch.autograd.grad(loss, params, allow_unused=True)
+    for p, g in zip(params, grads):
+        p.grad = g
+
+
 class ReconFitterBase:
     """The kernel-backed subset of recon/recon_fit_base.py:ReconFitterBase."""
 
@@ -72,7 +120,10 @@ class ReconFitterBase:
         if no_rand:
             return ReconFitterBase.project_so3(rot)
         if noise is None:
-            noise = torch.rand(rot.shape[0], 3, 3)            # CPU generator, like the reference
+            if torch.cuda.is_current_stream_capturing():
+                noise = torch.rand(rot.shape[0], 3, 3, device=rot.device)    # graph-safe device RNG
+            else:
+                noise = torch.rand(rot.shape[0], 3, 3)            # CPU generator, like the reference
         return ReconFitterBase.project_so3(rot + 1e-4 * noise.to(rot.device))
 
     def transform_obj_verts(self, verts, obj_R, obj_t, obj_s):
@@ -143,3 +194,97 @@ class ReconFitterBehave(ReconFitterBase):
         if "pose_init" in data_dict:
             loss_dict["pinit"] = torch.mean(torch.sum((smpl.pose[:, 3:72] - data_dict["pose_init"]) ** 2, -1))
         return loss_dict
+
+
+class FusedFitSteps:
+    """The two inner optimisation steps of the fitting loop with NO autograd graph: explicit forward kernels,
+    closed-form loss gradients (a handful of elementwise torch ops under no_grad) and explicit adjoint kernels,
+    so a step is  LBS -> field query -> dL/d(preds) -> query adjoint -> LBS adjoint -> Adam  (SMPL phase,
+    recon/recon_fit_behave.py:293-337 field terms) or  SO(3) -> rigid -> query -> dL/d(preds) -> query adjoint
+    -> rigid adjoint -> SO(3) adjoint -> Adam  ('object only' phase, recon/recon_fit_behave.py:165-198).
+    Both are plain stream-ordered launches, hence capturable in a CUDA graph (`graphed()`).
+
+    The reference queries the object points twice per step (recon_fit_behave.py:179 + recon_fit_base.py:515);
+    the two queries have identical inputs, so one forward + one adjoint launch (heads df and centers) gives the
+    same losses and gradients.  Loss weights / decay are those of get_loss_weights()."""
+
+    W = {"object": 30.0 ** 2, "part": 0.05 ** 2, "scale": 10.0 ** 2, "df_h": 30.0 ** 2, "ocent": 15 ** 2, "pinit": 5 ** 2}
+
+    def __init__(self, net, smpl, data_dict, obj_R, obj_t, obj_s, lr_smpl=0.006, lr_obj=0.006, obj_scale=1.0, decay=1.0):
+        self.net, self.smpl, self.data = net, smpl, data_dict
+        self.R, self.t, self.s = obj_R, obj_t, obj_s
+        self.obj_scale, self.decay = obj_scale, decay
+        self.smpl_params = [smpl.trans, smpl.global_pose, smpl.body_pose, smpl.top_betas, smpl.other_betas]
+        self.opt_smpl = torch.optim.Adam(self.smpl_params, lr_smpl, capturable=True)
+        self.opt_obj = torch.optim.Adam([obj_t, obj_R, obj_s], lr_obj, capturable=True)
+        self.h_net = net.handle
+        self.h_lbs = smpl.smpl.handle
+        self.h_aux = _lib.get_handle(obj_t.device)
+        self.cc = data_dict["query_dict"]["crop_center"].detach().float().contiguous()
+
+    @torch.no_grad()
+    def smpl_step(self):
+        sm, d = self.smpl, self.data
+        feat, skip = self.net._maps()
+        pose = torch.cat([sm.global_pose, sm.body_pose, sm.hand_pose], 1)
+        betas = torch.cat([sm.top_betas, sm.other_betas], 1)
+        trans, off = sm.trans.detach(), sm.offsets.detach()
+        verts, _, _, _ = self.h_lbs.lbs_fwd(pose, betas, trans, off, want_posed=False)
+        (df, _, parts, _), _ = self.h_net.query_fwd(feat, skip, verts, self.cc, _lib.HEAD_DF | _lib.HEAD_PARTS)
+        B, _, N = df.shape
+        k = 1.0 / (1.0 + self.decay)
+        # L = w_dfh * mean(min(df_h, 0.1)) + w_part * mean_b sum_n CE(parts, labels)
+        dfh = df[:, 0]
+        logp = torch.log_softmax(parts, 1)
+        labels = d["part_labels"]
+        loss = self.W["df_h"] * k * torch.clamp(dfh, max=0.1).mean() - self.W["part"] * k * logp.gather(1, labels.unsqueeze(1)).sum() / B
+        g_df = torch.zeros_like(df)
+        g_df[:, 0] = (dfh <= 0.1).float() * (self.W["df_h"] * k / (B * N))
+        g_parts = logp.exp()
+        g_parts.scatter_add_(1, labels.unsqueeze(1), torch.full_like(labels, -1, dtype=g_parts.dtype).unsqueeze(1))
+        g_parts *= self.W["part"] * k / B
+        g_verts = self.h_net.query_bwd(feat, skip, verts, self.cc, [g_df, None, g_parts, None])
+        g_pose, g_betas, g_trans, _ = self.h_lbs.lbs_bwd(pose, betas, trans, off, g_verts, None, False)
+        if "pose_init" in d:     # 5^2 * mean_b sum (pose[3:72] - pose_init)^2
+            diff = pose[:, 3:72] - d["pose_init"]
+            loss = loss + self.W["pinit"] * k * (diff ** 2).sum(-1).mean()
+            g_pose[:, 3:72] += self.W["pinit"] * k * 2.0 / B * diff
+        sm.trans.grad, sm.global_pose.grad, sm.body_pose.grad = g_trans, g_pose[:, :3].contiguous(), g_pose[:, 3:66].contiguous()
+        sm.top_betas.grad, sm.other_betas.grad = g_betas[:, :2].contiguous(), g_betas[:, 2:].contiguous()
+        self.opt_smpl.step()
+        return loss
+
+    @torch.no_grad()
+    def object_step(self, noise: Optional[torch.Tensor] = None):
+        d = self.data
+        feat, skip = self.net._maps()
+        obj0 = d["objects"]
+        B, N, _ = obj0.shape
+        if noise is None:
+            noise = torch.rand(B, 3, 3, device=obj0.device)
+        rot_in = (self.R + 1e-4 * noise).contiguous()                        # decopose_axis (recon_fit_base.py:373-384)
+        Rm = self.h_aux.project_so3(rot_in)
+        t, s = self.t.detach(), self.s.detach()
+        obj = self.h_aux.rigid_fwd(obj0, Rm, t, s)
+        (df, _, _, cen), _ = self.h_net.query_fwd(feat, skip, obj, self.cc, _lib.HEAD_DF | _lib.HEAD_CENTERS)
+        k = 1.0 / (1.0 + self.decay)
+        dfo = df[:, 1]
+        dvec = obj.mean(1) - d["smpl_center"] - cen[:, 3:].mean(-1)          # (B,3)
+        loss = (self.W["object"] * k * torch.clamp(dfo, max=0.8).mean() + self.W["scale"] * k * ((s - self.obj_scale) ** 2).mean()
+                + self.W["ocent"] * k * (dvec ** 2).sum(-1).mean())
+        g_df = torch.zeros_like(df)
+        g_df[:, 1] = (dfo <= 0.8).float() * (self.W["object"] * k / (B * N))
+        g_cen = torch.zeros_like(cen)
+        coef = self.W["ocent"] * k * 2.0 / (B * N)
+        g_cen[:, 3:] = (-coef * dvec).unsqueeze(-1)
+        g_obj = self.h_net.query_bwd(feat, skip, obj, self.cc, [g_df, None, None, g_cen])
+        g_obj += (coef * dvec).unsqueeze(1)
+        g_R, g_t, g_s, _ = self.h_aux.rigid_bwd(obj0, Rm, t, s, g_obj, False)
+        g_s += self.W["scale"] * k * 2.0 / B * (s - self.obj_scale)
+        self.R.grad, self.t.grad, self.s.grad = self.h_aux.project_so3_bwd(rot_in, g_R), g_t, g_s
+        self.opt_obj.step()
+        return loss
+
+    def graphed(self):
+        """(smpl_step, object_step) captured in CUDA graphs; each call replays one optimisation step."""
+        return GraphedStep(self.smpl_step), GraphedStep(self.object_step)

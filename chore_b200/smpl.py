@@ -131,8 +131,10 @@ class SMPLPyTorchWrapperBatchSplitParams(nn.Module):
         self.hand_pose = mk(hand_pose, (batch_sz, hand_num))
         self.trans = mk(trans, (batch_sz, 3))
         self.offsets = mk(offsets, (batch_sz, nv, 3))
-        self.betas = torch.cat([self.top_betas, self.other_betas], 1)
-        self.pose = torch.cat([self.global_pose, self.body_pose, self.hand_pose], 1)
+        with torch.no_grad():   # values only: building an autograd graph here would bind the parameters' grad
+            # accumulators to the construction-time (legacy default) stream and break CUDA-graph capture
+            self.betas = torch.cat([self.top_betas, self.other_betas], 1)
+            self.pose = torch.cat([self.global_pose, self.body_pose, self.hand_pose], 1)
         self.faces, self.gender, self.hands, self.device = faces, gender, hands, device
         self.smpl = model
         self.regressors = regressors

@@ -421,3 +421,45 @@ def test_smpl_fit_step_vs_oracle(net, sd, smpl_layer):
                                                             verts.grad.contiguous().to(DEV), None, False)
     assert rel_err(g_trans, t.grad) < 2e-4 and rel_err(g_betas, b.grad) < 2e-4, (rel_err(g_trans, t.grad), rel_err(g_betas, b.grad))
     assert rel_err(g_pose, p.grad) < 2e-4, rel_err(g_pose, p.grad)
+
+
+def test_fused_fit_steps_match_autograd_path(net, smpl_layer):
+    """FusedFitSteps (explicit adjoint kernels, no autograd graph, CUDA-graph replay) == the autograd-Function
+    path (forward_smpl / forward_step + backward): same losses and the same parameter gradients."""
+    import chore_b200
+    feat, tmpx = O.synth_features(71, B=1)
+    set_maps(net, feat, tmpx)
+    gen = torch.Generator().manual_seed(72)
+    mk = lambda: chore_b200.SMPLPyTorchWrapperBatchSplitParams.from_smpl(chore_b200.SMPLPyTorchWrapperBatch(
+        smpl_layer, 1, betas=0.3 * torch.randn(1, 10, generator=torch.Generator().manual_seed(1)),
+        pose=0.1 * torch.randn(1, 156, generator=torch.Generator().manual_seed(2)), trans=torch.tensor([[0.0, 0.1, 2.2]]), device=DEV))
+    labels = torch.randint(14, (1, 6890), generator=gen).to(DEV)
+    obj = (0.2 * torch.randn(1, 5000, 3, generator=gen)).to(DEV)
+    noise = torch.rand(1, 3, 3, generator=gen).to(DEV)
+    data = {"net": net, "query_dict": {"crop_center": torch.tensor([[1008., 995.]], device=DEV)}, "part_labels": labels,
+            "objects": obj, "smpl_center": torch.tensor([[0.0, 0.1, 2.2]], device=DEV)}
+    mkobj = lambda: ((torch.eye(3).unsqueeze(0) + 0.05 * torch.randn(1, 3, 3, generator=torch.Generator().manual_seed(3))).to(DEV).requires_grad_(True),
+                     torch.tensor([[0.2, 0.1, 2.3]], device=DEV, requires_grad=True), torch.full((1,), 1.05, device=DEV, requires_grad=True))
+    fit = chore_b200.ReconFitterBehave(device=DEV)
+    w = fit.get_loss_weights()
+    # autograd path
+    sa = mk(); Ra, ta, sca = mkobj()
+    la = fit.sum_dict(fit.forward_smpl(sa, data), w, 1); la.backward()
+    lo = fit.sum_dict(fit.forward_step(net, sa, data, Ra, ta, sca, "object only", noise=noise), w, 1); lo.backward()
+    # fused path, learning rate 0 so that the parameters stay put
+    sf = mk(); Rf, tf, scf = mkobj()
+    fused = chore_b200.FusedFitSteps(net, sf, data, Rf, tf, scf, lr_smpl=0.0, lr_obj=0.0)
+    lf = fused.smpl_step(); lfo = fused.object_step(noise)
+    assert rel_err(lf, la) < 1e-5 and rel_err(lfo, lo) < 1e-5, (lf.item(), la.item(), lfo.item(), lo.item())
+    for name in ("trans", "global_pose", "body_pose", "top_betas", "other_betas"):
+        assert rel_err(getattr(sf, name).grad, getattr(sa, name).grad) < 1e-4, name
+    for a, b, name in ((Rf, Ra, "R"), (tf, ta, "t"), (scf, sca, "s")):
+        assert rel_err(a.grad, b.grad) < 1e-4, (name, rel_err(a.grad, b.grad))
+    # CUDA-graph replay: the loss decreases over 30 replayed Adam steps
+    sg = mk(); Rg, tg, scg = mkobj()
+    g_smpl, g_obj = chore_b200.FusedFitSteps(net, sg, data, Rg, tg, scg, lr_smpl=0.006, lr_obj=0.006).graphed()
+    first = (float(g_smpl()), float(g_obj()))
+    for _ in range(30):
+        g_smpl(); g_obj()
+    last = (float(g_smpl()), float(g_obj()))
+    assert last[0] < first[0] and last[1] < first[1], (first, last)
