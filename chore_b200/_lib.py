@@ -41,6 +41,8 @@ SIGNATURES = {
     "chore_encode": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "chore_query_fwd": (_I, [_P, _P, _P, _I, _I, _P, _P, _I, _I, _U32, _P, _P, _P, _P, _P, _P]),
     "chore_query_bwd": (_I, [_P, _P, _P, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "chore_query_bwd_workspace_bytes": (C.c_size_t, [_I, _I]),
+    "chore_query_bwd_ws": (_I, [_P, _P, _P, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "chore_query_grid": (_I, [_P, _P, _P, _I, _I, _P, _I, C.POINTER(_I), C.POINTER(C.c_float), C.POINTER(C.c_float),
                               _I64, _I64, _U32, _P, _P, _P, _P, _P]),
     "chore_lbs_load_model": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I]),
@@ -173,10 +175,14 @@ class Handle:
         g_points = torch.empty_like(points)
         if N == 0:
             return g_points
+        # scratch comes from torch's allocator: stable under CUDA-graph capture (graph-private pool)
+        nbytes = int(self.lib.chore_query_bwd_workspace_bytes(B, N))
+        ws = torch.empty(max(nbytes, 4) // 4, dtype=torch.float32, device=points.device)
         with torch.cuda.device(self.device):
-            self._check(self.lib.chore_query_bwd(self.h, feat.data_ptr(), skip.data_ptr(), feat.shape[1], feat.shape[2],
-                                                 points.data_ptr(), crop_center.data_ptr(), B, N,
-                                                 *[_ptr(g) for g in grads], g_points.data_ptr(), _stream()))
+            self._check(self.lib.chore_query_bwd_ws(self.h, feat.data_ptr(), skip.data_ptr(), feat.shape[1], feat.shape[2],
+                                                    points.data_ptr(), crop_center.data_ptr(), B, N,
+                                                    *[_ptr(g) for g in grads], g_points.data_ptr(), ws.data_ptr(), nbytes,
+                                                    _stream()))
         return g_points
 
     def query_grid(self, feat, skip, crop_center, b: int, res, b_min, b_max, start: int, count: int,

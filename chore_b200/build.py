@@ -57,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcuda"]
+    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]   # no -lcuda: must dlopen on CPU-only boxes
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")

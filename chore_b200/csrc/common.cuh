@@ -60,6 +60,7 @@ struct MlpWeights {
     float *w4 = nullptr;    // [4][16][128]  rows >= n_out zero
     float *b4 = nullptr;    // [4][16]
     unsigned char *wstream = nullptr;   // tensor-core path: per-tile stream of pre-swizzled fp16 hi/lo panels
+    unsigned char *wstream_bwd = nullptr;   // 4 per-head streams for the tensor-core backward
     bool loaded = false;
 };
 
@@ -105,6 +106,8 @@ struct chore_handle {
     size_t ws_bytes = 0;
     void *ws2 = nullptr;
     size_t ws2_bytes = 0;
+    void *bwd_ws = nullptr;      // query backward: gX scratch (B*N, 384)
+    size_t bwd_ws_bytes = 0;
     void *lbs_ws = nullptr;      // LBS / rigid intermediates (own buffer: may interleave with encode)
     size_t lbs_ws_bytes = 0;
     std::vector<void *> owned;   // device allocations released by chore_destroy
@@ -122,6 +125,9 @@ int query_tc_launch(chore_handle *h, const float *feat, const float *skip, int f
                     const float *crop_center, int B, long long N, long long n_start, long long n_count, int grid_mode,
                     int batch_index, const int *res, const double *step, const double *bmin, unsigned head_mask,
                     float *const outs[4], unsigned char *in_img, cudaStream_t st);
+int query_bwd_tc_launch(chore_handle *h, const float *feat, const float *skip, int fh, int fw, const float *points,
+                        const float *crop_center, int B, long long N, const float *const g_heads[4], float *g_points,
+                        void *workspace, size_t workspace_bytes, cudaStream_t st);
 bool query_use_tensor_cores();   // CHORE_B200_QUERY=simt selects the fp32 SIMT kernel
 
 // tensor-core encoder convolutions (conv_tc.cu)

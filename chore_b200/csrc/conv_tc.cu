@@ -203,15 +203,36 @@ __global__ void __launch_bounds__(kThreadsConv, 1) conv_tc_kernel(const __grid_c
     }
 }
 
-// driver entry point for cuTensorMapEncodeTiled (resolved once; libcuda is linked)
+// cuTensorMapEncodeTiled is resolved through the runtime (cudaGetDriverEntryPoint) so that the library
+// does not link libcuda.so: it must still dlopen on a CPU-only build box.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
 int make_map(CUtensorMap *map, const void *base, int Cp, int W, int H, int B) {
     const cuuint64_t gdim[4] = {(cuuint64_t)Cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     const cuuint64_t gstride[3] = {(cuuint64_t)Cp * 2, (cuuint64_t)W * Cp * 2, (cuuint64_t)H * W * Cp * 2};
     const cuuint32_t box[4] = {64, (cuuint32_t)kPatchW, (cuuint32_t)kPatchH, 1};
     const cuuint32_t estride[4] = {1, 1, 1, 1};
-    const CUresult r = cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(base), gdim, gstride, box,
-                                              estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) {
+        chore_set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return CHORE_ERR_CUDA;
+    }
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(base), gdim, gstride, box, estride,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         chore_set_error("cuTensorMapEncodeTiled failed with %d (Cp=%d W=%d H=%d B=%d)", (int)r, Cp, W, H, B);
         return CHORE_ERR_CUDA;

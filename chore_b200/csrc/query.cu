@@ -702,13 +702,22 @@ extern "C" int chore_query_grid(chore_handle *h, const float *feat, const float 
     return launch_fwd<64>(q, 1, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int chore_query_bwd(chore_handle *h, const float *feat, const float *skip, int fh, int fw,
-                               const float *points, const float *crop_center, int B, int N, const float *g_df,
-                               const float *g_pca, const float *g_parts, const float *g_centers,
-                               float *g_points, void *stream) {
+extern "C" size_t chore_query_bwd_workspace_bytes(int B, int N) {
+    return query_use_tensor_cores() ? (size_t)B * (size_t)N * 384 * sizeof(float) : 0;
+}
+
+extern "C" int chore_query_bwd_ws(chore_handle *h, const float *feat, const float *skip, int fh, int fw,
+                                  const float *points, const float *crop_center, int B, int N, const float *g_df,
+                                  const float *g_pca, const float *g_parts, const float *g_centers, float *g_points,
+                                  void *workspace, size_t workspace_bytes, void *stream) {
     if (int rc = check_maps(h, feat, skip, fh, fw)) return rc;
     CHORE_CHECK(points && crop_center && g_points && B > 0 && N >= 0, "bad points / crop_center / g_points");
     if (N == 0) return CHORE_OK;
+    if (query_use_tensor_cores() && getenv("CHORE_B200_QUERY_BWD_SIMT") == nullptr) {
+        const float *const gh[4] = {g_df, g_pca, g_parts, g_centers};
+        return query_bwd_tc_launch(h, feat, skip, fh, fw, points, crop_center, B, N, gh, g_points, workspace, workspace_bytes,
+                                   static_cast<cudaStream_t>(stream));
+    }
     constexpr int P = 32;
     QueryParams q{};
     q.feat = feat; q.skip = skip; q.fh = fh; q.fw = fw;
@@ -726,4 +735,13 @@ extern "C" int chore_query_bwd(chore_handle *h, const float *feat, const float *
     dim3 grid((unsigned)((N + P - 1) / P), (unsigned)B);
     CHORE_LAUNCH(query_bwd_kernel<P>, grid, NT, smem, static_cast<cudaStream_t>(stream), q);
     return CHORE_OK;
+}
+
+extern "C" int chore_query_bwd(chore_handle *h, const float *feat, const float *skip, int fh, int fw,
+                               const float *points, const float *crop_center, int B, int N, const float *g_df,
+                               const float *g_pca, const float *g_parts, const float *g_centers,
+                               float *g_points, void *stream) {
+    // handle-owned scratch (grows on demand; use chore_query_bwd_ws under CUDA-graph capture)
+    return chore_query_bwd_ws(h, feat, skip, fh, fw, points, crop_center, B, N, g_df, g_pca, g_parts, g_centers, g_points,
+                              nullptr, 0, stream);
 }

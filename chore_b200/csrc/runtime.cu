@@ -67,6 +67,7 @@ extern "C" void chore_destroy(chore_handle *h) {
     if (h->ws) cudaFree(h->ws);
     if (h->ws2) cudaFree(h->ws2);
     if (h->lbs_ws) cudaFree(h->lbs_ws);
+    if (h->bwd_ws) cudaFree(h->bwd_ws);
     delete h;
 }
 

@@ -105,6 +105,15 @@ int chore_query_bwd(chore_handle *h, const float *feat, const float *skip, int f
                     const float *g_df, const float *g_pca, const float *g_parts,
                     const float *g_centers, float *g_points, void *stream);
 
+/* Same with caller-owned scratch of chore_query_bwd_workspace_bytes(B, N) bytes (may be 0): required when the
+ * call is captured in a CUDA graph, because the scratch pointer is baked into the captured launches. */
+size_t chore_query_bwd_workspace_bytes(int B, int N);
+int chore_query_bwd_ws(chore_handle *h, const float *feat, const float *skip, int fh, int fw,
+                       const float *points, const float *crop_center, int B, int N,
+                       const float *g_df, const float *g_pca, const float *g_parts,
+                       const float *g_centers, float *g_points, void *workspace,
+                       size_t workspace_bytes, void *stream);
+
 /* dense grid of model/sdf.py:4-48 (create_grid + batch_eval) evaluated without
  * materialising the coordinates: point i = (ix*ry + iy)*rz + iz (np.mgrid order),
  * coord = b_min + (b_max-b_min)/res * idx.  Evaluates points [start, start+count). */

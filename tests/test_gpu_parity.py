@@ -362,7 +362,7 @@ def test_fit_object_only_step_vs_golden(net, sd):
     # (1) identical points: per-point gradient of the whole loss
     p_c = obj_o.detach().contiguous().to(DEV).requires_grad_(True)
     fit.sum_dict(losses_of(q_cuda, p_c, data["smpl_center"], T(f["s"])), fit.get_loss_weights(), int(f["it"])).backward()
-    grad_close(p_c.grad, obj_o.grad, tol=2e-5, frac=0.999, worst=0.5)
+    grad_close(p_c.grad, obj_o.grad, tol=1e-4, frac=0.999, worst=0.5)
     # (2) identical R: rigid transform + queries + losses, gradients to (R, t, s)
     R_c = R_o.detach().to(DEV).requires_grad_(True)
     t2, s2 = (T(f[k]).clone().requires_grad_(True) for k in ("t", "s"))
@@ -415,7 +415,7 @@ def test_smpl_fit_step_vs_oracle(net, sd, smpl_layer):
     l1 = {"df_h": torch.clamp(df_c[:, 0:1, :], max=0.1).mean(),
           "part": torch.nn.functional.cross_entropy(parts_c, labels.to(DEV), reduction="none").sum(-1).mean()}
     fit.sum_dict(l1, fit.get_loss_weights(), 1).backward()
-    grad_close(v_c.grad, verts.grad, tol=2e-5, frac=0.999, worst=0.5)
+    grad_close(v_c.grad, verts.grad, tol=1e-4, frac=0.999, worst=0.5)
     # stage 2: identical vertex gradients -> LBS adjoint
     g_pose, g_betas, g_trans, _ = smpl_layer.handle.lbs_bwd(pose0.to(DEV), betas0.to(DEV), trans0.to(DEV), None,
                                                             verts.grad.contiguous().to(DEV), None, False)
