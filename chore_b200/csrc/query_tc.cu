@@ -137,6 +137,50 @@ __device__ __forceinline__ TapsTc make_taps_tc(float nx, float ny, int H, int W)
     return t;
 }
 
+// One 64-channel k-block of the A operand for the 32 rows of gather warp g: a half-warp owns one point
+// (16 lanes x 4 channels), and the 4 bilinear taps of kGatherBatch points are issued back to back before any of
+// them is consumed, so kGatherBatch * 4 independent 16-byte loads per lane cover the L2 latency (the previous
+// one-point-at-a-time loop paid one full L2 round trip per point and left the MMA warp waiting on a_full).
+// Arithmetic is unchanged: v = sum_k tap_k * w_k in tap order nw, ne, sw, se, invalid taps contribute exactly 0.
+constexpr int kGatherBatch = 4;
+__device__ __forceinline__ void gather_kblock(const float *__restrict__ base, int H, int W, int C, float my_nx, float my_ny,
+                                              int g, int half, int l16, uint8_t *hi, uint8_t *lo) {
+#pragma unroll 1
+    for (int it0 = 0; it0 < 16; it0 += kGatherBatch) {
+        float4 v[kGatherBatch][4];
+        float wgt[kGatherBatch][4];
+#pragma unroll
+        for (int j = 0; j < kGatherBatch; ++j) {
+            const int src = (it0 + j) * 2 + half;
+            const float nx = __shfl_sync(0xffffffffu, my_nx, src), ny = __shfl_sync(0xffffffffu, my_ny, src);
+            const TapsTc t = make_taps_tc(nx, ny, H, W);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                wgt[j][k] = t.w[k];
+                v[j][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t.valid & (1u << k))
+                    v[j][k] = __ldg(reinterpret_cast<const float4 *>(base + ((size_t)(t.y0 + (k >> 1)) * W + (t.x0 + (k & 1))) * C));
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kGatherBatch; ++j) {
+            const int r = g * 32 + (it0 + j) * 2 + half;
+            float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                v0 = fmaf(v[j][k].x, wgt[j][k], v0); v1 = fmaf(v[j][k].y, wgt[j][k], v1);
+                v2 = fmaf(v[j][k].z, wgt[j][k], v2); v3 = fmaf(v[j][k].w, wgt[j][k], v3);
+            }
+            uint32_t h01, l01, h23, l23;
+            split2(v0, v1, h01, l01);
+            split2(v2, v3, h23, l23);
+            const uint32_t off = sw128(r, l16 >> 1) + (l16 & 1) * 8;
+            *reinterpret_cast<uint2 *>(hi + off) = make_uint2(h01, h23);
+            *reinterpret_cast<uint2 *>(lo + off) = make_uint2(l01, l23);
+        }
+    }
+}
+
 struct Bars {
     uint64_t a_full[kNA], a_empty[kNA];
     uint64_t w_full[kNW], w_empty[kNW];
@@ -356,29 +400,8 @@ __global__ void __launch_bounds__(kThreads, 1) query_tc_kernel(const TcParams q)
                 uint8_t *hi = ringA + (size_t)sa * kStageA, *lo = hi + kPanelBytes;
                 if (kb < 5) {
                     const bool is_feat = kb < 4;
-                    const int H = is_feat ? q.fh : 2 * q.fh, W = is_feat ? q.fw : 2 * q.fw, C = is_feat ? kFeatC : kSkipC;
-                    const float *base = (is_feat ? F + kb * 64 : S) + l16 * 4;
-#pragma unroll 4
-                    for (int it = 0; it < 16; ++it) {
-                        const int src = it * 2 + half, r = g * 32 + src;
-                        const float nx = __shfl_sync(0xffffffffu, my_nx, src), ny = __shfl_sync(0xffffffffu, my_ny, src);
-                        const TapsTc t = make_taps_tc(nx, ny, H, W);
-                        float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            if (t.valid & (1u << k)) {
-                                const float4 v = __ldg(reinterpret_cast<const float4 *>(base + ((size_t)(t.y0 + (k >> 1)) * W + (t.x0 + (k & 1))) * C));
-                                v0 = fmaf(v.x, t.w[k], v0); v1 = fmaf(v.y, t.w[k], v1);
-                                v2 = fmaf(v.z, t.w[k], v2); v3 = fmaf(v.w, t.w[k], v3);
-                            }
-                        }
-                        uint32_t h01, l01, h23, l23;
-                        split2(v0, v1, h01, l01);
-                        split2(v2, v3, h23, l23);
-                        const uint32_t off = sw128(r, l16 >> 1) + (l16 & 1) * 8;
-                        *reinterpret_cast<uint2 *>(hi + off) = make_uint2(h01, h23);
-                        *reinterpret_cast<uint2 *>(lo + off) = make_uint2(l01, l23);
-                    }
+                    gather_kblock((is_feat ? F + kb * 64 : S) + l16 * 4, is_feat ? q.fh : 2 * q.fh, is_feat ? q.fw : 2 * q.fw,
+                                  is_feat ? kFeatC : kSkipC, my_nx, my_ny, g, half, l16, hi, lo);
                 } else {
                     // z_feat = [x, y, z - 2.2] (model/chore.py:128-129) + 13 zero channels: one k-step, lane = row
                     const int r = g * 32 + lane;
@@ -666,29 +689,8 @@ __global__ void __launch_bounds__(kThreads, 1) query_bwd_tc_kernel(const TcParam
                 uint8_t *hi = ringA + (size_t)sa * kStageA, *lo = hi + kPanelBytes;
                 if (kb < 5) {
                     const bool is_feat = kb < 4;
-                    const int H = is_feat ? q.fh : 2 * q.fh, W = is_feat ? q.fw : 2 * q.fw, C = is_feat ? kFeatC : kSkipC;
-                    const float *base = (is_feat ? F + kb * 64 : S) + l16 * 4;
-#pragma unroll 4
-                    for (int it = 0; it < 16; ++it) {
-                        const int src = it * 2 + half, r = g * 32 + src;
-                        const float nx = __shfl_sync(0xffffffffu, my_nx, src), ny = __shfl_sync(0xffffffffu, my_ny, src);
-                        const TapsTc t = make_taps_tc(nx, ny, H, W);
-                        float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            if (t.valid & (1u << k)) {
-                                const float4 v = __ldg(reinterpret_cast<const float4 *>(base + ((size_t)(t.y0 + (k >> 1)) * W + (t.x0 + (k & 1))) * C));
-                                v0 = fmaf(v.x, t.w[k], v0); v1 = fmaf(v.y, t.w[k], v1);
-                                v2 = fmaf(v.z, t.w[k], v2); v3 = fmaf(v.w, t.w[k], v3);
-                            }
-                        }
-                        uint32_t h01, l01, h23, l23;
-                        split2(v0, v1, h01, l01);
-                        split2(v2, v3, h23, l23);
-                        const uint32_t off = sw128(r, l16 >> 1) + (l16 & 1) * 8;
-                        *reinterpret_cast<uint2 *>(hi + off) = make_uint2(h01, h23);
-                        *reinterpret_cast<uint2 *>(lo + off) = make_uint2(l01, l23);
-                    }
+                    gather_kblock((is_feat ? F + kb * 64 : S) + l16 * 4, is_feat ? q.fh : 2 * q.fh, is_feat ? q.fw : 2 * q.fw,
+                                  is_feat ? kFeatC : kSkipC, my_nx, my_ny, g, half, l16, hi, lo);
                 } else {
                     const int r = g * 32 + lane;
                     uint32_t h01, l01, h23, l23;
