@@ -48,6 +48,9 @@ SIGNATURES = {
     "chore_lbs_load_model": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I]),
     "chore_lbs_fwd": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P]),
     "chore_lbs_bwd": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "chore_landmarks_load": (_I, [_P, _P, _P, _P, _I, _I, _I]),
+    "chore_landmarks_fwd": (_I, [_P, _P, _I, _P, _P]),
+    "chore_landmarks_bwd": (_I, [_P, _P, _I, _P, _I, _P]),
     "chore_rigid_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P]),
     "chore_rigid_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "chore_project_so3": (_I, [_P, _P, _I, _P, _P]),
@@ -231,6 +234,40 @@ class Handle:
                                                B, g_verts.data_ptr(), _ptr(g_jtr), g_pose.data_ptr(), g_betas.data_ptr(),
                                                g_trans.data_ptr(), _ptr(g_off), _stream()))
         return g_pose, g_betas, g_trans, g_off
+
+    # ---- landmark regressors -------------------------------------------------------------------
+    def landmarks_load(self, rowptr, col, val, L: int, V: int) -> None:
+        """CSR (host) of the stacked (L,V) regressor matrix."""
+        rowptr = torch.as_tensor(rowptr).to(torch.int32).contiguous().cpu()
+        col = torch.as_tensor(col).to(torch.int32).contiguous().cpu()
+        val = torch.as_tensor(val).to(torch.float32).contiguous().cpu()
+        with torch.cuda.device(self.device):
+            self._check(self.lib.chore_landmarks_load(self.h, rowptr.data_ptr(), col.data_ptr(), val.data_ptr(),
+                                                      int(L), int(V), int(val.numel())))
+        self.lmk_shape = (int(L), int(V))
+
+    def landmarks_fwd(self, verts):
+        check_cuda(verts)
+        L, V = self.lmk_shape
+        if verts.shape[1] != V or verts.shape[2] != 3:
+            raise ChoreError(f"verts must be (B,{V},3), got {tuple(verts.shape)}")
+        out = torch.empty(verts.shape[0], L, 3, device=verts.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.chore_landmarks_fwd(self.h, verts.data_ptr(), verts.shape[0], out.data_ptr(), _stream()))
+        return out
+
+    def landmarks_bwd(self, g_out, g_verts: Optional[torch.Tensor] = None):
+        """g_out (B,L,3) -> g_verts (B,V,3); accumulates into `g_verts` when one is given."""
+        g_out = g_out.contiguous()
+        check_cuda(g_out, g_verts)
+        L, V = self.lmk_shape
+        acc = g_verts is not None
+        if g_verts is None:
+            g_verts = torch.empty(g_out.shape[0], V, 3, device=g_out.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.chore_landmarks_bwd(self.h, g_out.data_ptr(), g_out.shape[0], g_verts.data_ptr(), int(acc),
+                                                     _stream()))
+        return g_verts
 
     # ---- rigid object ------------------------------------------------------------------------
     def rigid_fwd(self, verts, R, t, s):

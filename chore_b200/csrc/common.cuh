@@ -95,12 +95,23 @@ struct LbsModel {
     bool loaded = false;
 };
 
+// ---- landmark regressors (body25 | face | hand rows stacked), CSR and its transpose ------------------
+struct LandmarkModel {
+    int L = 0, V = 0, nnz = 0;
+    int32_t *rowptr = nullptr, *col = nullptr;     // [L+1], [nnz]   landmarks <- vertices
+    float *val = nullptr;
+    int32_t *t_rowptr = nullptr, *t_col = nullptr; // [V+1], [nnz]   vertices <- landmarks (adjoint, no atomics)
+    float *t_val = nullptr;
+    bool loaded = false;
+};
+
 struct chore_handle {
     int device = 0;
     int sm_count = 148;
     MlpWeights mlp;
     EncoderWeights enc;
     LbsModel lbs;
+    LandmarkModel lmk;
     // growable scratch (encoder activations, LBS intermediates)
     void *ws = nullptr;
     size_t ws_bytes = 0;

@@ -581,6 +581,51 @@ int lbs_fill(chore_handle *h, LbsParams &p, int B) {
     return CHORE_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// landmark regressors: Y[b, r, :] (+)= sum_k val[k] * X[b, col[k], :] over the CSR row r.
+// Replaces batch_sparse_dense_matmul (lib_smpl/torch_functions.py:52-76), which the reference calls three
+// times per get_landmarks() with a Python loop over the batch (lib_smpl/wrapper_pytorch.py:78-90).
+// Forward: one warp per landmark (hundreds of non-zeros per row).  Adjoint: one thread per vertex over the
+// transposed CSR (a handful of non-zeros per row), so no atomics and a deterministic sum order.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) spmm3_warp_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                                                         const float *__restrict__ val, int rows, int cols, int B,
+                                                         const float *__restrict__ X, float *__restrict__ Y) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= rows * B) return;
+    const int b = w / rows, r = w - b * rows;
+    const float *x = X + (size_t)b * cols * 3;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int k = rowptr[r] + lane; k < rowptr[r + 1]; k += 32) {
+        const float v = __ldg(val + k);
+        const float *p = x + (size_t)__ldg(col + k) * 3;
+        a0 = fmaf(v, __ldg(p), a0); a1 = fmaf(v, __ldg(p + 1), a1); a2 = fmaf(v, __ldg(p + 2), a2);
+    }
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+    if (lane == 0) {
+        float *y = Y + ((size_t)b * rows + r) * 3;
+        y[0] = a0; y[1] = a1; y[2] = a2;
+    }
+}
+
+__global__ void __launch_bounds__(256) spmm3_thread_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                                                           const float *__restrict__ val, int rows, int cols, int B,
+                                                           const float *__restrict__ X, float *__restrict__ Y, int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * B) return;
+    const int b = i / rows, r = i - b * rows;
+    const float *x = X + (size_t)b * cols * 3;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) {
+        const float v = __ldg(val + k);
+        const float *p = x + (size_t)__ldg(col + k) * 3;
+        a0 = fmaf(v, __ldg(p), a0); a1 = fmaf(v, __ldg(p + 1), a1); a2 = fmaf(v, __ldg(p + 2), a2);
+    }
+    float *y = Y + ((size_t)b * rows + r) * 3;
+    if (accumulate) { a0 += y[0]; a1 += y[1]; a2 += y[2]; }
+    y[0] = a0; y[1] = a1; y[2] = a2;
+}
+
 }   // namespace
 
 extern "C" int chore_lbs_load_model(chore_handle *h, const float *v_template, const float *shapedirs,
@@ -706,5 +751,58 @@ extern "C" int chore_project_so3_bwd(chore_handle *h, const float *mats, const f
                                      void *stream) {
     CHORE_CHECK(h && mats && g_out && g_mats && B > 0, "null argument");
     CHORE_LAUNCH(project_so3_bwd_kernel, (B + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream), mats, g_out, B, g_mats);
+    return CHORE_OK;
+}
+
+// ---- landmark regressors ---------------------------------------------------------------------------
+extern "C" int chore_landmarks_load(chore_handle *h, const int32_t *rowptr, const int32_t *col, const float *val,
+                                    int L, int V, int nnz) {
+    CHORE_CHECK(h && rowptr && col && val && L > 0 && V > 0 && nnz > 0, "bad landmark regressor (L=%d V=%d nnz=%d)", L, V, nnz);
+    CHORE_CHECK(rowptr[0] == 0 && rowptr[L] == nnz, "rowptr does not span [0, nnz]");
+    CHORE_CUDA(cudaSetDevice(h->device));
+    for (int r = 0; r < L; ++r) CHORE_CHECK(rowptr[r] <= rowptr[r + 1], "rowptr is not monotone at row %d", r);
+    for (int k = 0; k < nnz; ++k) CHORE_CHECK(col[k] >= 0 && col[k] < V, "column index %d out of range at entry %d", col[k], k);
+    // transpose (counting sort by column; rows stay ascending inside a column => deterministic adjoint order)
+    std::vector<int32_t> trow(V + 1, 0), tcol(nnz);
+    std::vector<float> tval(nnz);
+    for (int k = 0; k < nnz; ++k) ++trow[col[k] + 1];
+    for (int v = 0; v < V; ++v) trow[v + 1] += trow[v];
+    std::vector<int32_t> fill(trow.begin(), trow.end() - 1);
+    for (int r = 0; r < L; ++r)
+        for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) {
+            const int d = fill[col[k]]++;
+            tcol[d] = r; tval[d] = val[k];
+        }
+    LandmarkModel &m = h->lmk;
+    auto up = [&](void **dst, const void *src, size_t bytes) -> int {
+        if (int rc = chore_dev_alloc(h, dst, bytes)) return rc;
+        CHORE_CUDA(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+        return CHORE_OK;
+    };
+    if (up(reinterpret_cast<void **>(&m.rowptr), rowptr, (size_t)(L + 1) * 4) || up(reinterpret_cast<void **>(&m.col), col, (size_t)nnz * 4) ||
+        up(reinterpret_cast<void **>(&m.val), val, (size_t)nnz * 4) || up(reinterpret_cast<void **>(&m.t_rowptr), trow.data(), (size_t)(V + 1) * 4) ||
+        up(reinterpret_cast<void **>(&m.t_col), tcol.data(), (size_t)nnz * 4) || up(reinterpret_cast<void **>(&m.t_val), tval.data(), (size_t)nnz * 4))
+        return CHORE_ERR_CUDA;
+    m.L = L; m.V = V; m.nnz = nnz; m.loaded = true;
+    return CHORE_OK;
+}
+
+extern "C" int chore_landmarks_fwd(chore_handle *h, const float *verts, int B, float *out, void *stream) {
+    CHORE_CHECK(h && verts && out && B > 0, "bad arguments");
+    const LandmarkModel &m = h->lmk;
+    if (!m.loaded) { chore_set_error("landmark regressors not loaded (chore_landmarks_load)"); return CHORE_ERR_NO_WEIGHTS; }
+    const int warps = m.L * B;
+    CHORE_LAUNCH(spmm3_warp_kernel, (warps * 32 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream), m.rowptr, m.col, m.val,
+                 m.L, m.V, B, verts, out);
+    return CHORE_OK;
+}
+
+extern "C" int chore_landmarks_bwd(chore_handle *h, const float *g_out, int B, float *g_verts, int accumulate, void *stream) {
+    CHORE_CHECK(h && g_out && g_verts && B > 0, "bad arguments");
+    const LandmarkModel &m = h->lmk;
+    if (!m.loaded) { chore_set_error("landmark regressors not loaded (chore_landmarks_load)"); return CHORE_ERR_NO_WEIGHTS; }
+    const int n = m.V * B;
+    CHORE_LAUNCH(spmm3_thread_kernel, (n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream), m.t_rowptr, m.t_col, m.t_val,
+                 m.V, m.L, B, g_out, g_verts, accumulate);
     return CHORE_OK;
 }

@@ -5,14 +5,19 @@ Mirrors, with the same names and argument meaning (paths relative to /root/refer
       recon/recon_fit_base.py:167-188,361-384
   ReconFitterBase.sum_dict, compute_obj_loss, compute_df_h_loss, compute_smpl_center_pred
       recon/recon_fit_base.py:351-359,513-551
-  ReconFitterBehave.get_loss_weights, forward_step ('object only'), forward_smpl (field terms)
-      recon/recon_fit_behave.py:165-222,293-358
-Out of scope: the silhouette phase (neural_renderer + detectron2), the
-joint-phase contact / collision terms (pytorch3d, torch-mesh-isect), keypoint and prior terms.
+  ReconFitterBase.compute_prior_loss, smplz_loss, compute_kpts_loss, project_points, projection_loss,
+      split_smpl, copy_smpl_params, get_smpl_bbox, get_smpl_height, get_loss_str
+      recon/recon_fit_base.py:230-231,345-349,522-535,653-700
+  th_Mahalanobis / Prior / HandPrior   lib_smpl/th_smpl_prior.py:19-60, lib_smpl/th_hand_prior.py:20-78
+  ReconFitterBehave.get_loss_weights, forward_step ('object only'), forward_smpl (all terms),
+      optimize_smpl, optimize_smpl_object ('object only' phase)
+      recon/recon_fit_behave.py:90-163,165-222,224-358
+Out of scope: the silhouette phase (neural_renderer + detectron2) and the
+joint-phase contact / collision terms (pytorch3d, torch-mesh-isect).
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, Optional
+from typing import Callable, Dict, Optional, Tuple
 
 import torch
 import torch.nn.functional as F
@@ -47,6 +52,56 @@ class _So3Fn(torch.autograd.Function):
     def backward(ctx, g_out):
         (m,) = ctx.saved_tensors
         return ctx.handle.project_so3_bwd(m, g_out), None
+
+
+class MahalanobisPrior:
+    """th_Mahalanobis (lib_smpl/th_smpl_prior.py:25-44): ||(pose[:, prefix:end] - mean) @ prec||^2 per batch row."""
+
+    def __init__(self, mean, prec, prefix: int = 3, end: int = 66, device="cuda:0"):
+        self.mean = torch.as_tensor(mean, dtype=torch.float32).reshape(1, -1).to(device)
+        self.prec = torch.as_tensor(prec, dtype=torch.float32).to(device)
+        self.prefix, self.end = prefix, end
+
+    def __call__(self, pose, prior_weight: float = 1.0):
+        temp = pose[:, self.prefix:self.end] - self.mean
+        temp2 = torch.matmul(temp, self.prec) * prior_weight
+        return (temp2 * temp2).sum(dim=1)
+
+
+class HandPrior:
+    """HandPrior(type='grab') (lib_smpl/th_hand_prior.py:47-78): left / right hand Mahalanobis terms on
+    pose[:, 66:] (2 x 45)."""
+    HAND_POSE_NUM = 45
+
+    def __init__(self, mean, lhand_prec, rhand_prec, prefix: int = 66, device="cuda:0"):
+        self.prefix = prefix
+        self.mean = torch.as_tensor(mean, dtype=torch.float32).reshape(1, -1).to(device)
+        self.lhand_prec = torch.as_tensor(lhand_prec, dtype=torch.float32).unsqueeze(0).to(device)
+        self.rhand_prec = torch.as_tensor(rhand_prec, dtype=torch.float32).unsqueeze(0).to(device)
+
+    def __call__(self, full_pose):
+        """Shapes as in the reference (:69-78): the precisions are (1,45,45), so the products are (1,B,45),
+        the concatenation along dim 1 is (1,2B,45) and the result is (1,45) -- summed over batch and hands,
+        NOT one value per batch row; torch.mean() of it is total / 45.  Kept for parity."""
+        temp = full_pose[:, self.prefix:] - self.mean
+        lhand = torch.matmul(temp[:, :self.HAND_POSE_NUM], self.lhand_prec)
+        rhand = torch.matmul(temp[:, self.HAND_POSE_NUM:], self.rhand_prec)
+        temp2 = torch.cat([lhand, rhand], 1)
+        return (temp2 * temp2).sum(dim=1)
+
+
+def load_priors(assets_root: str, device="cuda:0") -> Tuple[MahalanobisPrior, HandPrior]:
+    """get_prior() + HandPrior('grab') of the reference (lib_smpl/th_smpl_prior.py:19-52,
+    lib_smpl/th_hand_prior.py:20-45), read ONCE from `assets_root`/priors/*.pkl -- the reference
+    un-pickles all three files on every optimisation step (recon/recon_fit_base.py:530,534)."""
+    import pickle as pkl
+    from os.path import join
+    import numpy as np
+    rd = lambda n: pkl.load(open(join(assets_root, "priors", n), "rb"), encoding="latin1")
+    body, lh, rh = rd("body_prior.pkl"), rd("lh_prior.pkl"), rd("rh_prior.pkl")
+    body_prior = MahalanobisPrior(np.asarray(body["mean"]).astype("float32"), np.asarray(body["precision"]).astype("float32"), device=device)
+    hand_prior = HandPrior(np.concatenate([lh["mean"], rh["mean"]], 0), lh["precision"], rh["precision"], device=device)
+    return body_prior, hand_prior
 
 
 class GraphedStep:
@@ -100,11 +155,23 @@ def backward_to(loss: torch.Tensor, params) -> None:
 class ReconFitterBase:
     """The kernel-backed subset of recon/recon_fit_base.py:ReconFitterBase."""
 
-    def __init__(self, device="cuda:0", obj_scale: float = 1.0, debug: bool = False):
+    def __init__(self, device="cuda:0", obj_scale: float = 1.0, debug: bool = False, priors=None,
+                 net_in_size: int = 512, crop_size: float = 1200.0, strict: bool = False):
+        """priors: (MahalanobisPrior, HandPrior) from load_priors(), or None.  net_in_size / crop_size:
+        args.net_img_size[0] / KinectColorCamera(args.loadSize).crop_size (recon_fit_base.py:74-75).
+        strict: raise when forward_smpl lacks the priors / landmark regressors / data_dict entries its
+        non-field terms need (the reference always has them); otherwise those terms are left out."""
         self.device = device
         self.obj_scale = obj_scale
         self.debug = debug
         self.z_0 = 2.2
+        self.priors = priors
+        self.net_in_size = net_in_size
+        self.crop_size = float(crop_size)
+        self.strict = strict
+        # KinectColorCamera pixel intrinsics (model/camera.py:26-40)
+        self.fx_px, self.fy_px = 979.7844 / 2048. * 2048, 979.840 / 2048. * 2048
+        self.cx_px, self.cy_px = 1018.952 / 2048. * 2048, 779.486 / 2048. * 2048
 
     # ---- SO(3) / rigid helpers ----------------------------------------------------------------
     @staticmethod
@@ -151,6 +218,75 @@ class ReconFitterBase:
         loss_dict["df_h"] = torch.clamp(df_pred[:, 0:1, :], max=0.1).mean()
         return df_pred, parts_pred, centers_pred
 
+    def compute_prior_loss(self, loss_dict, smpl, nobeta: bool = False):
+        """recon_fit_base.py:522-535 with the priors loaded once (self.priors)."""
+        if self.priors is None:
+            raise RuntimeError("no SMPL priors: construct the fitter with priors=load_priors(assets_root)")
+        prior, hand_prior = self.priors
+        if not nobeta:
+            loss_dict["beta"] = torch.mean(smpl.betas ** 2)
+        loss_dict["pose"] = torch.mean(prior(smpl.pose[:, :72]))
+        loss_dict["hand"] = torch.mean(hand_prior(smpl.pose))
+
+    def smplz_loss(self, J, loss_dict):
+        """recon_fit_base.py:230-231: the depth of body25 joint 8 (mid hip) stays at z_0."""
+        loss_dict["smplz"] = torch.mean((J[:, 8, 2] - self.z_0) ** 2)
+
+    def project_points(self, joints3d, crop_center=None):
+        """recon_fit_base.py:661-670 + KinectColorCamera.project_screen (model/camera.py:51-71)."""
+        x, y, z = joints3d[:, :, 0:1], joints3d[:, :, 1:2], joints3d[:, :, 2:3]
+        px = self.fx_px * x / z + self.cx_px
+        py = self.fy_px * y / z + self.cy_px
+        if crop_center is not None:
+            px = self.crop_size / 2 + px - crop_center[:, 0].unsqueeze(1).unsqueeze(1)
+            py = self.crop_size / 2 + py - crop_center[:, 1].unsqueeze(1).unsqueeze(1)
+        return torch.cat([px, py], -1) * self.net_in_size / self.crop_size
+
+    def projection_loss(self, joints3d, joints2d, crop_center):
+        """recon_fit_base.py:672-676: confidence-weighted squared pixel distance."""
+        joints_proj = self.project_points(joints3d, crop_center)
+        loss = F.mse_loss(joints_proj[:, :, :2], joints2d[:, :, :2], reduction="none")
+        return torch.mean(torch.sum(loss, dim=-1) * joints2d[:, :, 2])
+
+    def compute_kpts_loss(self, data_dict, loss_dict, smpl, J=None):
+        """recon_fit_base.py:653-659.  `J` (body25 joints of this step) may be passed in to avoid the
+        reference's third LBS + regressor pass of the step."""
+        if J is None:
+            J = smpl.get_landmarks()[0]
+        loss_dict["j2d"] = self.projection_loss(J, data_dict["body_kpts"], data_dict["query_dict"]["crop_center"])
+
+    @staticmethod
+    def split_smpl(smpl):
+        from .smpl import SMPLPyTorchWrapperBatchSplitParams
+        return SMPLPyTorchWrapperBatchSplitParams.from_smpl(smpl)
+
+    @staticmethod
+    def copy_smpl_params(split_smpl, smpl):
+        """recon_fit_base.py:682-690 (other_betas are not copied there either)."""
+        smpl.pose.data[:, :3] = split_smpl.global_pose.data
+        smpl.pose.data[:, 3:66] = split_smpl.body_pose.data
+        smpl.pose.data[:, 66:] = split_smpl.hand_pose.data
+        smpl.betas.data[:, :2] = split_smpl.top_betas.data
+        smpl.trans.data = split_smpl.trans.data
+        return smpl
+
+    @staticmethod
+    def get_smpl_bbox(smpl):
+        with torch.no_grad():
+            verts = smpl()[0]
+        return torch.min(verts, 1)[0], torch.max(verts, 1)[0]
+
+    def get_smpl_height(self, smpl):
+        bmin, bmax = self.get_smpl_bbox(smpl)
+        return bmax[:, 1] - bmin[:, 1]
+
+    @staticmethod
+    def get_loss_str(it, loss_dict, weight_dict, weight_decay) -> str:
+        """recon_fit_base.py:345-349; one device->host copy for the whole line instead of one .item() per term."""
+        keys = list(loss_dict)
+        vals = torch.stack([weight_dict[k](loss_dict[k], weight_decay).mean().detach() for k in keys]).tolist()
+        return "Iter: {}".format(it) + "".join(", {}: {:0.4f}".format(k, v) for k, v in zip(keys, vals))
+
     def compute_smpl_center_pred(self, data_dict, model, smpl):
         with torch.no_grad():
             smpl_verts = smpl()[0]
@@ -184,16 +320,97 @@ class ReconFitterBehave(ReconFitterBase):
         return loss_dict
 
     def forward_smpl(self, smpl, data_dict, phase="global"):
-        """Field terms of recon_fit_behave.py:293-337: df_h, part cross-entropy, fixed depth and
-        initial-pose regularisers (priors / 2D keypoints need external assets and are skipped)."""
+        """recon_fit_behave.py:293-337, every term: df_h, priors (pose, hand), part cross-entropy, fixed depth of
+        the mid hip (smplz), initial-pose regulariser (pinit) and, in phase 'kpts', the 2-D keypoint term (j2d).
+        The LBS runs ONCE per step: the landmark regressors are applied to the vertices of that same forward
+        (the reference runs a second and, in 'kpts', a third LBS inside get_landmarks, :305,315 and
+        recon_fit_base.py:649 -- same values).  Terms whose assets are absent are skipped unless self.strict."""
         loss_dict = {}
         model = data_dict["net"]
         smpl_verts, jtr, _, _ = smpl()
         _, parts_pred, _ = self.compute_df_h_loss(data_dict, loss_dict, model, smpl_verts)
+        if self.priors is not None:
+            self.compute_prior_loss(loss_dict, smpl, nobeta=True)
+        elif self.strict:
+            raise RuntimeError("forward_smpl: no SMPL priors (strict)")
         loss_dict["part"] = F.cross_entropy(parts_pred, data_dict["part_labels"], reduction="none").sum(-1).mean()
+        J = None
+        if getattr(smpl, "regressors", None) is not None:
+            J, _, _ = smpl.get_landmarks(smpl_verts)
+            self.smplz_loss(J, loss_dict)
+        elif self.strict:
+            raise RuntimeError("forward_smpl: the SMPL wrapper has no landmark regressors (strict)")
         if "pose_init" in data_dict:
             loss_dict["pinit"] = torch.mean(torch.sum((smpl.pose[:, 3:72] - data_dict["pose_init"]) ** 2, -1))
+        elif self.strict:
+            raise KeyError("pose_init")
+        if phase == "kpts":
+            if J is None:
+                raise RuntimeError("phase 'kpts' needs landmark regressors on the SMPL wrapper")
+            self.compute_kpts_loss(data_dict, loss_dict, smpl, J)
         return loss_dict
+
+    # ---- optimisation loops ---------------------------------------------------------------------
+    def optimize_smpl(self, smpl, data_dict, iter_for_betas=10, iter_for_pose=10, iter_for_kpts=5, steps_per_iter=10,
+                      max_iter=150, log: Optional[Callable[[str], None]] = None):
+        """recon_fit_behave.py:224-291: phase 'global' (top betas + translation, lr 0.02), then all poses
+        (lr 0.006), then 'kpts' until convergence.  Same schedule, decay and early-stop rule; the convergence
+        test is the only device->host sync of a step (the reference also syncs for its tqdm string)."""
+        smpl_split = self.split_smpl(smpl)
+        opt = torch.optim.Adam([smpl_split.top_betas, smpl_split.trans], lr=0.02)
+        height_init = self.get_smpl_height(smpl)
+        weight_dict = self.get_loss_weights()
+        prev_loss = 300.0
+        phase = "global"
+        for it in range(iter_for_betas + iter_for_kpts + iter_for_pose + max_iter):
+            opt.zero_grad()        # once per outer iteration, like the reference (:244): grads accumulate inside
+            if it == iter_for_betas:
+                phase = "smpl all pose"
+                opt = torch.optim.Adam([smpl_split.trans, smpl_split.global_pose, smpl_split.body_pose,
+                                        smpl_split.top_betas, smpl_split.other_betas], 0.006, betas=(0.9, 0.999))
+            elif it == iter_for_betas + iter_for_pose:
+                phase = "kpts"
+            for i in range(steps_per_iter):
+                loss_dict = self.forward_smpl(smpl_split, data_dict, phase)
+                decay = 1 if phase != "kpts" else it / 3
+                loss = self.sum_dict(loss_dict, weight_dict, decay)
+                loss.backward()
+                opt.step()
+                if log is not None:
+                    log(f"{phase}: " + self.get_loss_str(f"{it}-{i}", loss_dict, weight_dict, decay))
+                # early stop (:275-282); evaluated (one host sync) only inside the window where it can fire
+                if it > 0.25 * max_iter + iter_for_betas + iter_for_pose:
+                    lv, pv = float(loss.detach()), float(prev_loss)
+                    if abs(pv - lv) / pv < pv * 0.001:
+                        scale = self.get_smpl_height(smpl_split) / height_init
+                        return self.copy_smpl_params(smpl_split, smpl), scale
+                prev_loss = loss.detach()
+        scale = self.get_smpl_height(smpl_split) / height_init
+        return self.copy_smpl_params(smpl_split, smpl), scale
+
+    def optimize_smpl_object(self, model, data_dict, obj_iter=20, joint_iter=10, steps_per_iter=10,
+                             log: Optional[Callable[[str], None]] = None):
+        """recon_fit_behave.py:90-163, phase 'object only' (obj_iter x steps_per_iter Adam steps on
+        obj_t, obj_R, obj_s, lr 0.006, decay 1).  The 'sil' and 'joint' phases that follow in the reference
+        need the silhouette renderer and the contact / collision terms and are not run:
+        joint_iter is accepted for signature parity and ignored."""
+        smpl = data_dict["smpl"]
+        smpl_split = self.split_smpl(smpl)
+        data_dict["smpl"] = smpl_split
+        obj_R, obj_t, obj_s = data_dict["obj_R"], data_dict["obj_t"], data_dict["obj_s"]
+        opt = torch.optim.Adam([obj_t, obj_R, obj_s], lr=0.006)
+        weight_dict = self.get_loss_weights()
+        data_dict["smpl_center"] = self.compute_smpl_center_pred(data_dict, model, smpl)
+        for it in range(obj_iter):
+            opt.zero_grad()
+            for i in range(steps_per_iter):
+                loss_dict = self.forward_step(model, smpl_split, data_dict, obj_R, obj_t, obj_s, "object only")
+                loss = self.sum_dict(loss_dict, weight_dict, 1)
+                loss.backward()
+                opt.step()
+                if log is not None:
+                    log("optimizing object only " + self.get_loss_str(f"{it}-{i}", loss_dict, weight_dict, 1))
+        return smpl, data_dict["obj_R"], data_dict["obj_t"]
 
 
 class FusedFitSteps:
@@ -208,10 +425,16 @@ class FusedFitSteps:
     the two queries have identical inputs, so one forward + one adjoint launch (heads df and centers) gives the
     same losses and gradients.  Loss weights / decay are those of get_loss_weights()."""
 
-    W = {"object": 30.0 ** 2, "part": 0.05 ** 2, "scale": 10.0 ** 2, "df_h": 30.0 ** 2, "ocent": 15 ** 2, "pinit": 5 ** 2}
+    W = {"object": 30.0 ** 2, "part": 0.05 ** 2, "scale": 10.0 ** 2, "df_h": 30.0 ** 2, "ocent": 15 ** 2, "pinit": 5 ** 2,
+         "pose": 1e-5, "hand": 1e-5, "smplz": 30 ** 2, "j2d": 0.3 ** 2}
 
-    def __init__(self, net, smpl, data_dict, obj_R, obj_t, obj_s, lr_smpl=0.006, lr_obj=0.006, obj_scale=1.0, decay=1.0):
+    def __init__(self, net, smpl, data_dict, obj_R, obj_t, obj_s, lr_smpl=0.006, lr_obj=0.006, obj_scale=1.0, decay=1.0,
+                 fitter: Optional["ReconFitterBase"] = None, phase: str = "smpl all pose"):
+        """fitter: supplies the priors / camera constants for the pose-prior, hand-prior, smplz and (phase 'kpts')
+        2-D keypoint terms of forward_smpl; without it only the field terms (+ pinit) are used.  The landmark terms
+        need regressors on `smpl`."""
         self.net, self.smpl, self.data = net, smpl, data_dict
+        self.fitter, self.phase = fitter, phase
         self.R, self.t, self.s = obj_R, obj_t, obj_s
         self.obj_scale, self.decay = obj_scale, decay
         self.smpl_params = [smpl.trans, smpl.global_pose, smpl.body_pose, smpl.top_betas, smpl.other_betas]
@@ -244,7 +467,41 @@ class FusedFitSteps:
         g_parts.scatter_add_(1, labels.unsqueeze(1), torch.full_like(labels, -1, dtype=g_parts.dtype).unsqueeze(1))
         g_parts *= self.W["part"] * k / B
         g_verts = self.h_net.query_bwd(feat, skip, verts, self.cc, [g_df, None, g_parts, None])
+        fit = self.fitter
+        if getattr(sm, "regressors", None) is not None and fit is not None:
+            # smplz: 30^2 mean_b (J8.z - z0)^2; j2d ('kpts'): 0.3^2 mean_{b,j} conf ||proj(J) - kpts||^2 (recon_fit_base.py:230,653-676)
+            lm = sm.regressors.handle.landmarks_fwd(verts)
+            J = lm[:, :sm.regressors.sizes[0]]
+            g_lm = torch.zeros_like(lm)
+            dz = J[:, 8, 2] - fit.z_0
+            loss = loss + self.W["smplz"] * k * (dz ** 2).mean()
+            g_lm[:, 8, 2] = self.W["smplz"] * k * 2.0 / B * dz
+            if self.phase == "kpts":
+                sc = fit.net_in_size / fit.crop_size
+                x, y, z = J[..., 0], J[..., 1], J[..., 2]
+                px = (fit.fx_px * x / z + fit.cx_px + fit.crop_size / 2 - self.cc[:, 0:1]) * sc
+                py = (fit.fy_px * y / z + fit.cy_px + fit.crop_size / 2 - self.cc[:, 1:2]) * sc
+                kp = d["body_kpts"]
+                ex, ey, conf = px - kp[..., 0], py - kp[..., 1], kp[..., 2]
+                loss = loss + self.W["j2d"] * k * ((ex ** 2 + ey ** 2) * conf).mean()
+                c = self.W["j2d"] * k * 2.0 / (B * J.shape[1]) * conf * sc
+                gx, gy = c * ex * fit.fx_px / z, c * ey * fit.fy_px / z
+                nJ = J.shape[1]
+                g_lm[:, :nJ, 0] += gx
+                g_lm[:, :nJ, 1] += gy
+                g_lm[:, :nJ, 2] += -(gx * x + gy * y) / z
+            sm.regressors.handle.landmarks_bwd(g_lm, g_verts)          # g_verts += R^T g_lm
         g_pose, g_betas, g_trans, _ = self.h_lbs.lbs_bwd(pose, betas, trans, off, g_verts, None, False)
+        if fit is not None and fit.priors is not None:                  # Mahalanobis priors (recon_fit_base.py:522-535)
+            bp, hp = fit.priors
+            tb = (pose[:, bp.prefix:bp.end] - bp.mean) @ bp.prec
+            tl = (pose[:, hp.prefix:hp.prefix + 45] - hp.mean[:, :45]) @ hp.lhand_prec[0]
+            tr = (pose[:, hp.prefix + 45:] - hp.mean[:, 45:]) @ hp.rhand_prec[0]
+            # the hand term is total / 45 (see HandPrior.__call__), the body term a mean over the batch
+            loss = loss + self.W["pose"] * k * (tb ** 2).sum(1).mean() + self.W["hand"] * k * ((tl ** 2).sum() + (tr ** 2).sum()) / 45.0
+            g_pose[:, bp.prefix:bp.end] += self.W["pose"] * k * 2.0 / B * (tb @ bp.prec.t())
+            g_pose[:, hp.prefix:hp.prefix + 45] += self.W["hand"] * k * 2.0 / 45.0 * (tl @ hp.lhand_prec[0].t())
+            g_pose[:, hp.prefix + 45:] += self.W["hand"] * k * 2.0 / 45.0 * (tr @ hp.rhand_prec[0].t())
         if "pose_init" in d:     # 5^2 * mean_b sum (pose[3:72] - pose_init)^2
             diff = pose[:, 3:72] - d["pose_init"]
             loss = loss + self.W["pinit"] * k * (diff ** 2).sum(-1).mean()

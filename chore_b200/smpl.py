@@ -44,6 +44,67 @@ class _LbsFn(torch.autograd.Function):
         return g_pose, g_betas, g_trans, g_off, None
 
 
+class _LandmarkFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, verts, handle):
+        ctx.handle = handle
+        return handle.landmarks_fwd(verts.detach().contiguous().float())
+
+    @staticmethod
+    def backward(ctx, g_out):
+        return ctx.handle.landmarks_bwd(g_out), None
+
+
+def load_regressors(assets_root: str):
+    """lib_smpl/body_landmark.py:16-28 (batch_size=None branch): the body25 / face / hand regressor
+    pickles (scipy sparse, stored (V,L)) transposed to (L,V)."""
+    import pickle as pkl
+    from os.path import join
+    out = []
+    for name in ("body25_regressor.pkl", "face_regressor.pkl", "hand_regressor.pkl"):
+        with open(join(assets_root, name), "rb") as f:
+            out.append(pkl.load(f, encoding="latin1").T)
+    return tuple(out)
+
+
+def _to_csr(reg):
+    """One regressor (scipy sparse, torch sparse COO (optionally batched like the reference's stacked
+    tensors), or dense (L,V)) -> (rowptr, col, val, L, V) with duplicate entries summed."""
+    import numpy as np
+    import scipy.sparse as sp
+    if sp.issparse(reg):
+        m = sp.csr_matrix(reg)
+    elif torch.is_tensor(reg) and reg.is_sparse:
+        r = reg.coalesce()
+        idx, val = r.indices().cpu().numpy(), r.values().cpu().numpy()
+        if idx.shape[0] == 3:                       # (B,L,V) stack of identical matrices: take batch 0
+            keep = idx[0] == 0
+            idx, val = idx[1:, keep], val[keep]
+        m = sp.csr_matrix((val, (idx[0], idx[1])), shape=tuple(reg.shape[-2:]))
+    else:
+        m = sp.csr_matrix(np.asarray(torch.as_tensor(reg).detach().cpu().numpy()))
+    m.sum_duplicates()
+    m.sort_indices()
+    return m
+
+
+class LandmarkRegressors:
+    """The three landmark regressors stacked into one CSR matrix on the device (chore_landmarks_*)."""
+
+    def __init__(self, regressors, handle):
+        import scipy.sparse as sp
+        mats = [_to_csr(r) for r in regressors]
+        self.sizes = [m.shape[0] for m in mats]
+        full = sp.vstack(mats).tocsr()
+        full.sort_indices()
+        self.handle = handle
+        handle.landmarks_load(torch.from_numpy(full.indptr.astype("int32")), torch.from_numpy(full.indices.astype("int32")),
+                              torch.from_numpy(full.data.astype("float32")), full.shape[0], full.shape[1])
+
+    def __call__(self, verts):
+        return torch.split(_LandmarkFn.apply(verts, self.handle), self.sizes, dim=1)
+
+
 class SMPLHLayer(nn.Module):
     """SMPL_Layer.forward on the LBS kernels.  `forward(pose, th_betas, th_trans, th_offsets)`
     -> (verts, jtr, v_posed, naked) like smpl_layer.py:72-175 (hands=True, scale 1)."""
@@ -79,6 +140,12 @@ class SMPLHLayer(nn.Module):
         return _LbsFn.apply(th_pose_axisang, th_betas, th_trans, th_offsets, self.handle)
 
 
+def _make_regressors(regressors, model: "SMPLHLayer"):
+    if regressors is None or isinstance(regressors, LandmarkRegressors):
+        return regressors
+    return LandmarkRegressors(regressors, model.handle)
+
+
 class SMPLPyTorchWrapperBatch(nn.Module):
     """lib_smpl/wrapper_pytorch.py:23-90 with the LBS kernels underneath.  `model` is an
     SMPLHLayer (the reference passes a model_root and loads the pickle itself)."""
@@ -98,19 +165,20 @@ class SMPLPyTorchWrapperBatch(nn.Module):
         assert self.pose.shape[1] == npose, f"pose shape {tuple(self.pose.shape)} does not match hands={hands}"
         self.smpl = model
         self.faces = model.th_faces.clone()
-        # landmark regressors (lib_smpl/body_landmark.py:16-28): dense (L, V) matrices or None
-        self.regressors = regressors
+        # landmark regressors (lib_smpl/body_landmark.py:16-28): 3 x (L,V) sparse/dense matrices, an
+        # already-built LandmarkRegressors, or None
+        self.regressors = _make_regressors(regressors, model)
         self.to(device)
 
     def forward(self):
         return self.smpl(self.pose, th_betas=self.betas, th_trans=self.trans, th_offsets=self.offsets)
 
-    def get_landmarks(self):
+    def get_landmarks(self, verts=None):
         """body25 / face / hand landmarks = sparse regressors applied to the posed vertices
-        (wrapper_pytorch.py:78-90).  The regressors are tiny (<= 70 x 6890); torch.matmul."""
+        (wrapper_pytorch.py:78-90) in one CSR kernel.  The reference re-runs the LBS here; pass the
+        `verts` of a forward() of the same parameters to skip that second LBS (same values)."""
         assert self.regressors is not None, "no landmark regressors were given"
-        verts = self.forward()[0]
-        return tuple(torch.matmul(r.to(verts), verts) for r in self.regressors)
+        return self.regressors(self.forward()[0] if verts is None else verts)
 
 
 class SMPLPyTorchWrapperBatchSplitParams(nn.Module):
@@ -137,7 +205,7 @@ class SMPLPyTorchWrapperBatchSplitParams(nn.Module):
             self.pose = torch.cat([self.global_pose, self.body_pose, self.hand_pose], 1)
         self.faces, self.gender, self.hands, self.device = faces, gender, hands, device
         self.smpl = model
-        self.regressors = regressors
+        self.regressors = _make_regressors(regressors, model)
         self.to(device)
 
     def forward(self):
@@ -145,10 +213,10 @@ class SMPLPyTorchWrapperBatchSplitParams(nn.Module):
         self.pose = torch.cat([self.global_pose, self.body_pose, self.hand_pose], 1)
         return self.smpl(self.pose, th_betas=self.betas, th_trans=self.trans, th_offsets=self.offsets)
 
-    def get_landmarks(self):
+    def get_landmarks(self, verts=None):
+        """wrapper_pytorch.py:176-190; see SMPLPyTorchWrapperBatch.get_landmarks."""
         assert self.regressors is not None, "no landmark regressors were given"
-        verts = self.forward()[0]
-        return tuple(torch.matmul(r.to(verts), verts) for r in self.regressors)
+        return self.regressors(self.forward()[0] if verts is None else verts)
 
     @staticmethod
     def from_smpl(smpl: SMPLPyTorchWrapperBatch):

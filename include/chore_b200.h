@@ -142,6 +142,19 @@ int chore_lbs_bwd(chore_handle *h, const float *pose, const float *betas, const 
                   const float *offsets, int B, const float *g_verts, const float *g_jtr,
                   float *g_pose, float *g_betas, float *g_trans, float *g_offsets, void *stream);
 
+/* ---- landmark regressors: replaces batch_sparse_dense_matmul (lib_smpl/torch_functions.py:52-76)
+ *      as used by SMPLPyTorchWrapperBatch*.get_landmarks (lib_smpl/wrapper_pytorch.py:78-90): the
+ *      body25 (25), face (70) and hand (42) regressors of lib_smpl/body_landmark.py:16-28, stacked
+ *      row-wise into one (L,V) CSR matrix ------------------------------------------------- */
+/* rowptr (L+1), col (nnz), val (nnz): HOST pointers, landmarks <- vertices. */
+int chore_landmarks_load(chore_handle *h, const int32_t *rowptr, const int32_t *col, const float *val,
+                         int L, int V, int nnz);
+/* verts (B,V,3) -> out (B,L,3) */
+int chore_landmarks_fwd(chore_handle *h, const float *verts, int B, float *out, void *stream);
+/* adjoint: g_out (B,L,3) -> g_verts (B,V,3), overwritten or accumulated into (accumulate != 0) */
+int chore_landmarks_bwd(chore_handle *h, const float *g_out, int B, float *g_verts, int accumulate,
+                        void *stream);
+
 /* ---- rigid object transform: replaces ReconFitterBase.transform_obj_verts
  *      (recon/recon_fit_base.py:367-371): out = (verts @ R + t) * s --------------------- */
 /* verts (B,N,3), R (B,3,3), t (B,3), s (B) -> out (B,N,3) */

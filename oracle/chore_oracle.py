@@ -516,3 +516,55 @@ def smpl_losses(sd, feat, tmpx, crop_center, verts: Tensor, part_labels: Tensor)
     df, _, parts, _, _ = query(sd, feat, tmpx, verts, crop_center)
     return {"df_h": torch.clamp(df[:, 0:1, :], max=0.1).mean(),
             "part": F.cross_entropy(parts, part_labels, reduction="none").sum(-1).mean()}
+
+
+# ----------------------------------------------------------------------------------------
+# full SMPL-phase step (recon/recon_fit_behave.py:293-337 with recon_fit_base.py:230-231,522-542,653-676)
+# ----------------------------------------------------------------------------------------
+def mahalanobis(pose: Tensor, mean: Tensor, prec: Tensor, prefix: int = 3, end: int = 66) -> Tensor:
+    """th_Mahalanobis.__call__ (lib_smpl/th_smpl_prior.py:32-39)."""
+    t = torch.matmul(pose[:, prefix:end] - mean.view(1, -1), prec)
+    return (t * t).sum(dim=1)
+
+
+def hand_prior(pose: Tensor, mean: Tensor, lprec: Tensor, rprec: Tensor, prefix: int = 66) -> Tensor:
+    """HandPrior.__call__ (lib_smpl/th_hand_prior.py:69-78), including its shapes: the precisions carry a
+    leading 1, so the result is (1,45), summed over batch rows and both hands."""
+    temp = pose[:, prefix:] - mean.view(1, -1)
+    lh = torch.matmul(temp[:, :45], lprec.unsqueeze(0))
+    rh = torch.matmul(temp[:, 45:], rprec.unsqueeze(0))
+    t2 = torch.cat([lh, rh], 1)
+    return (t2 * t2).sum(dim=1)
+
+
+def project_to_input_image(joints3d: Tensor, crop_center: Tensor, net_in_size: int = 512) -> Tensor:
+    """ReconFitterBase.project_points (recon_fit_base.py:661-670) over KinectColorCamera.project_screen
+    (model/camera.py:51-71)."""
+    x, y, z = joints3d[:, :, 0:1], joints3d[:, :, 1:2], joints3d[:, :, 2:3]
+    px = FX_PX * x / z + CX_PX
+    py = FY_PX * y / z + CY_PX
+    px = CROP_SIZE / 2 + px - crop_center[:, 0].unsqueeze(1).unsqueeze(1)
+    py = CROP_SIZE / 2 + py - crop_center[:, 1].unsqueeze(1).unsqueeze(1)
+    return torch.cat([px, py], -1) * net_in_size / CROP_SIZE
+
+
+def smpl_full_losses(sd, feat, tmpx, crop_center, model: Dict[str, Tensor], pose: Tensor, betas: Tensor, trans: Tensor,
+                     part_labels: Tensor, pose_init: Tensor, regressors: Sequence[Tensor], priors: Dict[str, Tensor],
+                     body_kpts: Tensor | None = None, offsets: Tensor | None = None) -> Dict[str, Tensor]:
+    """forward_smpl, every term, in the reference's insertion order (sum_dict only sums, but keep it).
+    regressors: dense (L,V) body25 / face / hand; priors: body_mean, body_prec, hand_mean, lh_prec, rh_prec.
+    body_kpts given == phase 'kpts'."""
+    verts = lbs_forward(model, pose, betas, trans, offsets)[0]
+    df, _, parts, _, _ = query(sd, feat, tmpx, verts, crop_center)
+    out = {"df_h": torch.clamp(df[:, 0:1, :], max=0.1).mean(),
+           "pose": torch.mean(mahalanobis(pose[:, :72], priors["body_mean"], priors["body_prec"])),
+           "hand": torch.mean(hand_prior(pose, priors["hand_mean"], priors["lh_prec"], priors["rh_prec"])),
+           "part": F.cross_entropy(parts, part_labels, reduction="none").sum(-1).mean()}
+    J = torch.matmul(regressors[0], verts)
+    out["smplz"] = torch.mean((J[:, 8, 2] - Z0) ** 2)
+    out["pinit"] = torch.mean(torch.sum((pose[:, 3:72] - pose_init) ** 2, -1))
+    if body_kpts is not None:
+        proj = project_to_input_image(J, crop_center)
+        l2 = F.mse_loss(proj[:, :, :2], body_kpts[:, :, :2], reduction="none")
+        out["j2d"] = torch.mean(torch.sum(l2, dim=-1) * body_kpts[:, :, 2])
+    return out

@@ -20,6 +20,9 @@ Reference entry points exercised (paths relative to /root/reference):
   lib_smpl/smplpytorch/smplpytorch/pytorch/smpl_layer.py:72-175   SMPL_Layer.forward
   recon/recon_fit_base.py:167-188,367-384   project_so3 / transform_obj_verts / decopose_axis
   recon/recon_fit_behave.py:165-222          forward_step(phase='object only')
+  recon/recon_fit_behave.py:293-337          forward_smpl(phase='kpts'), with compute_prior_loss / smplz_loss /
+                                             compute_kpts_loss (recon_fit_base.py:230-231,522-535,653-676),
+                                             get_landmarks (lib_smpl/wrapper_pytorch.py:176-190)
 """
 from __future__ import annotations
 
@@ -196,6 +199,73 @@ def gold_rigid_and_fit(net):
          loss_ocent=losses["ocent"], total=total, grad_rot=rot.grad, grad_t=t.grad, grad_s=s.grad)
 
 
+def load_reference_assets():
+    """Landmark regressors and priors of the reference (assets/*.pkl) as plain arrays: the inputs of
+    fit_smpl_full.npz (stored in it, because /root/reference does not exist on the GPU box)."""
+    import pickle as pkl
+    import scipy.sparse as sp
+    root = os.path.join(ref_shim.REF_ROOT, "assets")
+    regs = []
+    for n in ("body25_regressor.pkl", "face_regressor.pkl", "hand_regressor.pkl"):
+        m = sp.csr_matrix(pkl.load(open(os.path.join(root, n), "rb"), encoding="latin1").T)
+        m.sum_duplicates(); m.sort_indices()
+        regs.append(m)
+    rd = lambda n: pkl.load(open(os.path.join(root, "priors", n), "rb"), encoding="latin1")
+    body, lh, rh = rd("body_prior.pkl"), rd("lh_prior.pkl"), rd("rh_prior.pkl")
+    pri = {"body_mean": np.asarray(body["mean"], np.float32), "body_prec": np.asarray(body["precision"], np.float32),
+           "hand_mean": np.concatenate([lh["mean"], rh["mean"]]).astype(np.float32),
+           "lh_prec": np.asarray(lh["precision"], np.float32), "rh_prec": np.asarray(rh["precision"], np.float32)}
+    return regs, pri
+
+
+def gold_fit_smpl_full(net):
+    """ReconFitterBehave.forward_smpl, phase 'kpts' (every term: df_h, pose / hand priors, part CE, smplz, pinit,
+    j2d), sum_dict with decay it/3 and backward to the split SMPL parameters -- recon/recon_fit_behave.py:265-271,
+    293-337.  The reference's own modules run unmodified; only the SMPL-H pickle is replaced by synthetic buffers
+    and `.cuda()` by a no-op (oracle/ref_shim.py)."""
+    import types as _t
+    Fitter = ref_shim.load_fitter_class()
+    from model.camera import KinectColorCamera
+    fit = object.__new__(Fitter)
+    fit.debug, fit.z_0, fit.obj_scale = False, 2.2, 1.0
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        fit.camera = KinectColorCamera(1200)
+    fit.net_in_size = 512
+    B = 2
+    buf = O.make_smplh_buffers(0)
+    g = torch.Generator().manual_seed(61)
+    pose = 0.15 * torch.randn(B, 156, generator=g)
+    betas = 0.5 * torch.randn(B, 10, generator=g)
+    trans = torch.tensor([[0.0, 0.0, 2.2]]) + 0.05 * torch.randn(B, 3, generator=g)
+    smpl = ref_shim.load_split_smpl(buf, B, pose, betas, trans)
+    sd = O.make_state_dict(0, "unit")
+    net.load_state_dict(sd)
+    feat, tmpx = O.synth_features(62, B=B)
+    net.im_feat_list, net.tmpx = [feat], tmpx
+    cc = torch.tensor([[1008., 995.], [1000., 980.]])
+    part_labels = torch.randint(14, (B, 6890), generator=g)
+    pose_init = pose[:, 3:72] + 0.05 * torch.randn(B, 69, generator=g)
+    kpts = torch.cat([512 * torch.rand(B, 25, 2, generator=g), torch.rand(B, 25, 1, generator=g)], -1)
+    data = {"net": net, "part_labels": part_labels, "pose_init": pose_init, "body_kpts": kpts,
+            "query_dict": {"crop_center": cc}}
+    it = 25
+    with ref_shim.cpu_priors():
+        losses = fit.forward_smpl(smpl, data, "kpts")
+    total = fit.sum_dict(losses, fit.get_loss_weights(), it / 3)
+    total.backward()
+    J, face, hands = smpl.get_landmarks()
+    regs, pri = load_reference_assets()
+    save("fit_smpl_full.npz", seed=61, weights_seed=0, buffers_seed=0, feat_seed=62, pose=pose, betas=betas, trans=trans,
+         crop_center=cc, part_labels=part_labels, pose_init=pose_init, body_kpts=kpts, decay=it / 3,
+         **{f"loss_{k}": v for k, v in losses.items()}, total=total, loss_order=np.array(list(losses)),
+         grad_trans=smpl.trans.grad, grad_global_pose=smpl.global_pose.grad, grad_body_pose=smpl.body_pose.grad,
+         grad_hand_pose=smpl.hand_pose.grad, grad_top_betas=smpl.top_betas.grad, grad_other_betas=smpl.other_betas.grad,
+         J=J, face=face, hands=hands,
+         **{f"reg{i}_{a}": getattr(m, a) for i, m in enumerate(regs) for a in ("indptr", "indices", "data")},
+         **{f"prior_{k}": v for k, v in pri.items()})
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
@@ -208,6 +278,7 @@ def main():
         gold_approx_surface(net)
         gold_lbs()
         gold_rigid_and_fit(net)
+        gold_fit_smpl_full(net)
 
 
 if __name__ == "__main__":

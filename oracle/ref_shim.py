@@ -128,3 +128,51 @@ def load_generator_class():
     with ref_cwd(), contextlib.redirect_stdout(open(os.devnull, "w")):
         from recon.generator import Generator
     return Generator
+
+
+def load_split_smpl(buffers, batch_sz, pose, betas, trans, assets_root=None):
+    """The reference's SMPLPyTorchWrapperBatchSplitParams (lib_smpl/wrapper_pytorch.py:93-190) around a
+    synthetic-buffer SMPL_Layer: __init__ would read the licensed SMPL-H pickle, so the module is built with
+    __new__ and given exactly the attributes __init__ sets (:108-160); forward / get_landmarks are the
+    reference's own code.  The landmark regressors are the reference's real assets."""
+    install()
+    import torch
+    import torch.nn as nn
+    with ref_cwd():
+        from lib_smpl.wrapper_pytorch import SMPLPyTorchWrapperBatchSplitParams
+        from lib_smpl.body_landmark import load_regressors
+        regs = load_regressors(assets_root or os.path.join(REF_ROOT, "assets"), batch_size=batch_sz)
+    m = SMPLPyTorchWrapperBatchSplitParams.__new__(SMPLPyTorchWrapperBatchSplitParams)
+    nn.Module.__init__(m)
+    m.top_betas = nn.Parameter(betas[:, :2].clone())
+    m.other_betas = nn.Parameter(betas[:, 2:].clone())
+    m.global_pose = nn.Parameter(pose[:, :3].clone())
+    m.body_pose = nn.Parameter(pose[:, 3:66].clone())
+    m.hand_pose = nn.Parameter(pose[:, 66:].clone())
+    m.trans = nn.Parameter(trans.clone())
+    m.offsets = nn.Parameter(torch.zeros(batch_sz, buffers["weights"].shape[0], 3))
+    m.betas = torch.cat([m.top_betas, m.other_betas], 1)
+    m.pose = torch.cat([m.global_pose, m.body_pose, m.hand_pose], 1)
+    m.faces, m.gender = None, "male"
+    m.smpl = load_smpl_layer(buffers)
+    m.body25_reg_torch, m.face_reg_torch, m.hand_reg_torch = regs
+    return m
+
+
+@contextlib.contextmanager
+def cpu_priors():
+    """compute_prior_loss (recon/recon_fit_base.py:522-535) moves the prior tensors to the GPU
+    unconditionally (th_smpl_prior.py:27-28 `.cuda()`, th_hand_prior.py:50 device='cuda:0').  In this
+    GPU-less container run the same code with `.cuda()` a no-op and HandPrior defaulting to the CPU."""
+    install()
+    import functools
+    import torch
+    with ref_cwd():
+        import recon.recon_fit_base as rfb
+    old_cuda, old_hp = torch.Tensor.cuda, rfb.HandPrior
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    rfb.HandPrior = functools.partial(old_hp, device="cpu")
+    try:
+        yield
+    finally:
+        torch.Tensor.cuda, rfb.HandPrior = old_cuda, old_hp

@@ -41,3 +41,12 @@ def rel_err(a, b):
     b = torch.as_tensor(b).double().cpu()
     scale = b.abs() + b.pow(2).mean().sqrt() + 1e-30
     return ((a - b).abs() / scale).max().item()
+
+
+def golden_smpl_assets(g):
+    """Landmark regressors (scipy CSR, (L,V)) and priors stored in fit_smpl_full.npz."""
+    import scipy.sparse as sp
+    regs = [sp.csr_matrix((g[f"reg{i}_data"], g[f"reg{i}_indices"], g[f"reg{i}_indptr"]), shape=(L, 6890))
+            for i, L in enumerate((25, 70, 42))]
+    pri = {k[len("prior_"):]: g[k] for k in g if k.startswith("prior_")}
+    return regs, pri

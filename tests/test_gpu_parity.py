@@ -484,3 +484,102 @@ def test_generator_gen_pc_batch_mechanics(net):
     assert out["pca_axis"].shape == (2, 3, 3) and out["centers"].shape == (2, 6)
     assert int(out["parts"].min()) >= 0 and int(out["parts"].max()) < 14
     assert torch.isfinite(out["points"]).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# full SMPL phase: landmark regressors, priors, smplz, 2-D keypoints, optimisation loops
+# ------------------------------------------------------------------------------------------------
+def _smpl_full_setup(net, smpl_layer, g):
+    import chore_b200
+    from conftest import golden_smpl_assets
+    regs, pri = golden_smpl_assets(g)
+    feat, tmpx = O.synth_features(int(g["feat_seed"]), B=2)
+    set_maps(net, feat, tmpx)
+    bp = chore_b200.fitter.MahalanobisPrior(pri["body_mean"], pri["body_prec"], device=DEV)
+    hp = chore_b200.fitter.HandPrior(pri["hand_mean"], pri["lh_prec"], pri["rh_prec"], device=DEV)
+    fit = chore_b200.ReconFitterBehave(device=DEV, priors=(bp, hp), strict=True)
+    w = chore_b200.SMPLPyTorchWrapperBatch(smpl_layer, 2, betas=g["betas"], pose=g["pose"], trans=g["trans"], device=DEV,
+                                           regressors=regs)
+    data = {"net": net, "part_labels": T(g["part_labels"]), "pose_init": T(g["pose_init"]), "body_kpts": T(g["body_kpts"]),
+            "query_dict": {"crop_center": T(g["crop_center"])}}
+    return fit, w, data, regs
+
+
+def test_landmarks_vs_golden(net, smpl_layer):
+    """get_landmarks (lib_smpl/wrapper_pytorch.py:176-190) on the CSR kernel: values against the reference's run,
+    adjoint against the dense transpose."""
+    g = load_golden("fit_smpl_full.npz")
+    fit, w, data, regs = _smpl_full_setup(net, smpl_layer, g)
+    J, face, hands = w.get_landmarks()
+    assert J.shape == (2, 25, 3) and face.shape == (2, 70, 3) and hands.shape == (2, 42, 3)
+    for got, name in ((J, "J"), (face, "face"), (hands, "hands")):
+        assert rel_err(got, g[name]) < 1e-5, name
+    gen = torch.Generator().manual_seed(5)
+    g_out = torch.randn(2, 137, 3, generator=gen)
+    dense = torch.from_numpy(np.vstack([r.toarray() for r in regs])).double()
+    want = torch.einsum("lv,blc->bvc", dense, g_out.double())
+    h = w.regressors.handle
+    got = h.landmarks_bwd(g_out.to(DEV))
+    assert rel_err(got, want) < 1e-5
+    acc = torch.ones(2, 6890, 3, device=DEV)
+    h.landmarks_bwd(g_out.to(DEV), acc)
+    assert rel_err(acc, want + 1.0) < 1e-5
+    # autograd reaches the SMPL parameters through the landmark kernel
+    w.zero_grad()
+    w.get_landmarks()[0][:, 8, 2].sum().backward()
+    assert w.trans.grad is not None and rel_err(w.trans.grad[:, 2], torch.ones(2)) < 1e-5
+
+
+def test_fit_smpl_full_step_vs_golden(net, smpl_layer):
+    """forward_smpl(phase='kpts') with every term of recon/recon_fit_behave.py:293-337 against the reference's own run:
+    each loss, the decayed sum, and the gradients to the split parameters (chained through query + LBS adjoints)."""
+    import chore_b200
+    g = load_golden("fit_smpl_full.npz")
+    fit, w, data, _ = _smpl_full_setup(net, smpl_layer, g)
+    split = fit.split_smpl(w)
+    losses = fit.forward_smpl(split, data, "kpts")
+    assert list(losses) == [str(k) for k in g["loss_order"]]
+    for k, v in losses.items():
+        assert rel_err(v, g[f"loss_{k}"]) < TOL, (k, float(v), float(g[f"loss_{k}"]))
+    total = fit.sum_dict(losses, fit.get_loss_weights(), float(g["decay"]))
+    assert rel_err(total, g["total"]) < TOL
+    total.backward()
+    # chained gradients: sums of thousands of per-vertex terms with ReLU / clamp gates (see the module docstring)
+    for name in ("trans", "global_pose", "body_pose", "hand_pose", "top_betas", "other_betas"):
+        assert rel_err(getattr(split, name).grad, g[f"grad_{name}"]) < 5e-2, (name, rel_err(getattr(split, name).grad, g[f"grad_{name}"]))
+    # the fused (autograd-free) step computes the same loss and the same gradients as the autograd path
+    split2 = fit.split_smpl(w)
+    R, t, s = torch.eye(3, device=DEV).repeat(2, 1, 1), torch.zeros(2, 3, device=DEV), torch.ones(2, device=DEV)
+    fused = chore_b200.FusedFitSteps(net, split2, data, R, t, s, lr_smpl=0.0, decay=float(g["decay"]), fitter=fit, phase="kpts")
+    lf = fused.smpl_step()
+    assert rel_err(lf, total) < 1e-5, (float(lf), float(total))
+    for name in ("trans", "global_pose", "body_pose", "top_betas", "other_betas"):
+        assert rel_err(getattr(split2, name).grad, getattr(split, name).grad) < 1e-4, name
+
+
+def test_optimize_loops_run_and_descend(net, smpl_layer):
+    """optimize_smpl / optimize_smpl_object (recon/recon_fit_behave.py:90-163,224-291) with a shortened schedule:
+    same phases, optimisers and decay; the weighted loss goes down and the parameters are copied back."""
+    g = load_golden("fit_smpl_full.npz")
+    fit, w, data, _ = _smpl_full_setup(net, smpl_layer, g)
+    logs = []
+    pose_before = w.pose.detach().clone()
+    smpl, scale = fit.optimize_smpl(w, data, iter_for_betas=2, iter_for_pose=2, iter_for_kpts=1, steps_per_iter=3, max_iter=1,
+                                    log=logs.append)
+    assert smpl is w and scale.shape == (2,) and torch.isfinite(scale).all()
+    # 6 outer x 3 inner steps unless the reference's early-stop rule fires inside the last ('kpts') iteration
+    assert 5 * 3 < len(logs) <= 6 * 3 and "j2d" in logs[-1] and "j2d" not in logs[0]
+    assert not torch.equal(w.pose.detach(), pose_before)
+    first = float(logs[6].split("df_h: ")[1].split(",")[0])       # first 'smpl all pose' step
+    last = float(logs[11].split("df_h: ")[1].split(",")[0])
+    assert last <= first + 0.05 * abs(first), (first, last)      # synthetic fields can be negative
+    gen = torch.Generator().manual_seed(9)
+    data.update({"smpl": w, "objects": (0.2 * torch.randn(2, 3000, 3, generator=gen)).to(DEV),
+                 "obj_R": (torch.eye(3).repeat(2, 1, 1) + 0.05 * torch.randn(2, 3, 3, generator=gen)).to(DEV).requires_grad_(True),
+                 "obj_t": torch.tensor([[0.2, 0.1, 2.3], [0.1, 0.0, 2.2]], device=DEV, requires_grad=True),
+                 "obj_s": torch.ones(2, device=DEV, requires_grad=True)})
+    logs = []
+    t0 = data["obj_t"].detach().clone()
+    out = fit.optimize_smpl_object(net, data, obj_iter=2, steps_per_iter=3, log=logs.append)
+    assert out[0] is w and len(logs) == 6 and "ocent" in logs[0]
+    assert data["smpl_center"].shape == (2, 3) and not torch.equal(data["obj_t"].detach(), t0)

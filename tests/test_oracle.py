@@ -150,3 +150,32 @@ def test_oracle_equals_live_reference(sd):
         net.query(pts, crop_center=cc)
     for a, b in zip(net.get_preds(), O.query(sd, feat, tmpx, pts, cc)[:4]):
         assert torch.equal(a, b)
+
+
+def test_fit_smpl_full_vs_golden(sd):
+    """forward_smpl(phase='kpts') with every term + sum_dict + backward to the split SMPL parameters:
+    the oracle restatement against the reference's own run (tests/golden/fit_smpl_full.npz)."""
+    from conftest import golden_smpl_assets
+    g = load_golden("fit_smpl_full.npz")
+    regs, pri = golden_smpl_assets(g)
+    regs_t = [T(r.toarray()).float() for r in regs]
+    pri_t = {k: T(v).float() for k, v in pri.items()}
+    buf = O.make_smplh_buffers(int(g["buffers_seed"]))
+    feat, tmpx = O.synth_features(int(g["feat_seed"]), B=2)
+    pose, betas, trans = (T(g[k]).clone().requires_grad_(True) for k in ("pose", "betas", "trans"))
+    losses = O.smpl_full_losses(sd, feat, tmpx, T(g["crop_center"]), buf, pose, betas, trans, T(g["part_labels"]),
+                                T(g["pose_init"]), regs_t, pri_t, body_kpts=T(g["body_kpts"]))
+    assert list(losses) == [str(k) for k in g["loss_order"]]
+    for k, v in losses.items():
+        assert rel_err(v, g[f"loss_{k}"]) < TOL, k
+    total = O.sum_dict(losses, float(g["decay"]))
+    assert rel_err(total, g["total"]) < TOL
+    total.backward()
+    gp = pose.grad
+    for name, got in (("trans", trans.grad), ("global_pose", gp[:, :3]), ("body_pose", gp[:, 3:66]), ("hand_pose", gp[:, 66:]),
+                      ("top_betas", betas.grad[:, :2]), ("other_betas", betas.grad[:, 2:])):
+        assert rel_err(got, g[f"grad_{name}"]) < 2e-4, name
+    # landmarks = sparse regressors applied to the posed vertices (wrapper_pytorch.py:176-190)
+    verts = O.lbs_forward(buf, T(g["pose"]), T(g["betas"]), T(g["trans"]))[0]
+    for r, name in zip(regs_t, ("J", "face", "hands")):
+        assert rel_err(torch.matmul(r, verts), g[name]) < TOL, name
