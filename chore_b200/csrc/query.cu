@@ -644,6 +644,7 @@ extern "C" int chore_query_fwd(chore_handle *h, const float *feat, const float *
     if (int rc = check_maps(h, feat, skip, fh, fw)) return rc;
     CHORE_CHECK(points && crop_center && B > 0 && N >= 0, "bad points / crop_center / sizes");
     head_mask &= CHORE_HEAD_ALL;
+    CHORE_CHECK(head_mask != 0, "head_mask selects no head");
     float *outs[kNumHeads] = {df, pca, parts, centers};
     for (int i = 0; i < kNumHeads; ++i)
         CHORE_CHECK(!(head_mask & (1u << i)) || outs[i], "output %d requested by head_mask is NULL", i);
@@ -677,6 +678,7 @@ extern "C" int chore_query_grid(chore_handle *h, const float *feat, const float 
                 "grid range [%lld, %lld) outside %lld points", (long long)start, (long long)(start + count),
                 (long long)total);
     head_mask &= CHORE_HEAD_ALL;
+    CHORE_CHECK(head_mask != 0, "head_mask selects no head");
     float *outs[kNumHeads] = {df, pca, parts, centers};
     for (int i = 0; i < kNumHeads; ++i)
         CHORE_CHECK(!(head_mask & (1u << i)) || outs[i], "output %d requested by head_mask is NULL", i);

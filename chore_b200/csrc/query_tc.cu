@@ -231,7 +231,10 @@ __global__ void __launch_bounds__(kThreads, 1) query_tc_kernel(const TcParams q)
         // the whole warp walks the loop (uniform control flow); one elected lane issues the copies
         uint32_t u = 0;   // running panel counter over all tiles
         for (long long tile = first_tile; tile < q.total_tiles; tile += tile_stride) {
-            for (int i = 0; i < kUnitsPerTile; ++i, ++u) {
+            for (int i = 0; i < kUnitsPerTile; ++i) {
+                // heads outside head_mask are not evaluated at all: their panels are never streamed
+                const int hd_i = i < kL1Blocks * 8 ? (i >> 1) & 3 : (i < kBigUnits ? ((i - kL1Blocks * 8) >> 2) & 3 : i - kBigUnits);
+                if (!((q.head_mask >> hd_i) & 1)) continue;
                 const int s = u % kNW;
                 mbar_wait_t(&bars->w_empty[s], ((u / kNW) & 1) ^ 1, DBG(0));
                 if (elect_one()) {
@@ -242,6 +245,7 @@ __global__ void __launch_bounds__(kThreads, 1) query_tc_kernel(const TcParams q)
                     bulk_g2s(ringW + (size_t)s * kPanelBytes, q.wstream + off, bytes, &bars->w_full[s]);
                 }
                 __syncwarp();
+                ++u;
             }
         }
     } else if (warp == 1) {
@@ -255,6 +259,7 @@ __global__ void __launch_bounds__(kThreads, 1) query_tc_kernel(const TcParams q)
         uint32_t ablk = 0;     // A ring block counter
         uint32_t actblk = 0;   // activation ring block counter
         uint32_t tile_i = 0;
+        const int last_head = 31 - __clz((int)(q.head_mask & 15u));     // the A stage is released after the last active head
         for (long long tile = first_tile; tile < q.total_tiles; tile += tile_stride, ++tile_i) {
             // ---- layer 1: 6 k-blocks x 4 heads, all four accumulators live ----
             for (int kb = 0; kb < kL1Blocks; ++kb, ++ablk) {
@@ -265,6 +270,7 @@ __global__ void __launch_bounds__(kThreads, 1) query_tc_kernel(const TcParams q)
                 const bool last = kb == kL1Blocks - 1;       // the xyz block holds 16 channels: one k-step
 #pragma unroll 1
                 for (int h = 0; h < 4; ++h) {
+                    if (!((q.head_mask >> h) & 1)) continue;
                     if (kb == 0) {   // accumulator of head h must have been drained (previous tile)
                         mbar_wait_t(&bars->tm_empty[h], (tile_i & 1) ^ 1, DBG(2));
                         tc_fence_after();
@@ -298,7 +304,7 @@ __global__ void __launch_bounds__(kThreads, 1) query_tc_kernel(const TcParams q)
                         }
                         umma_commit(&bars->w_empty[s1]);
                         if (last) umma_commit(&bars->tm_full[h]);       // layer-1 accumulator of head h complete
-                        if (h == 3) umma_commit(&bars->a_empty[sa]);
+                        if (h == last_head) umma_commit(&bars->a_empty[sa]);
                     }
                     __syncwarp();
                     u += 2;
@@ -309,6 +315,7 @@ __global__ void __launch_bounds__(kThreads, 1) query_tc_kernel(const TcParams q)
             for (int layer = 1; layer < 4; ++layer) {
 #pragma unroll 1
                 for (int h = 0; h < 4; ++h) {
+                    if (!((q.head_mask >> h) & 1)) continue;
                     const uint32_t d = tmem_base + h * 128;
                     // both activation blocks must be complete before the accumulator is overwritten
                     const uint32_t b0 = actblk, b1 = actblk + 1;
@@ -441,6 +448,7 @@ __global__ void __launch_bounds__(kThreads, 1) query_tc_kernel(const TcParams q)
             for (int layer = 0; layer < 4; ++layer) {
 #pragma unroll 1
                 for (int h = 0; h < 4; ++h) {
+                    if (!((q.head_mask >> h) & 1)) continue;             // head not requested: nothing was computed
                     if (layer == 3 && (h & 1) != colhalf) continue;      // last layer: the heads are split between the groups
                     mbar_wait_t(&bars->tm_full[h], layer & 1, DBG(7));   // 4 completions per tile: parity = layer & 1
                     tc_fence_after();
@@ -487,7 +495,7 @@ __global__ void __launch_bounds__(kThreads, 1) query_tc_kernel(const TcParams q)
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&bars->tm_empty[h]);   // the next tile's layer 1 may overwrite head h
-                        if (((q.head_mask >> h) & 1) && live) {
+                        if (live) {
                             float *outp = q.out[h] + ((size_t)b * nout) * q.N + q.n_start + n;
 #pragma unroll
                             for (int o = 0; o < 14; ++o) {

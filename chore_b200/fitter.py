@@ -23,6 +23,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib
+from .net import heads
 
 
 class _RigidFn(torch.autograd.Function):
@@ -206,14 +207,17 @@ class ReconFitterBase:
         return torch.stack([weight_dict[k](v, it) for k, v in loss_dict.items()]).sum()
 
     def compute_obj_loss(self, data_dict, loss_dict, model, obj_s, object):
-        model.query(object, **data_dict["query_dict"])
+        with heads(model, _lib.HEAD_DF):                    # only preds[0] is read below and by the callers
+            model.query(object, **data_dict["query_dict"])
         preds = model.get_preds()
         loss_dict["object"] = torch.clamp(preds[0][:, 1:2, :], max=0.8).mean()
         loss_dict["scale"] = torch.mean((obj_s - self.obj_scale) ** 2)
         return preds
 
     def compute_df_h_loss(self, data_dict, loss_dict, model, smpl_verts):
-        model.query(smpl_verts, **data_dict["query_dict"])
+        # centers_pred is only read by the reference's debug visualisation (recon_fit_behave.py:321-331)
+        with heads(model, _lib.HEAD_DF | _lib.HEAD_PARTS | (_lib.HEAD_CENTERS if self.debug else 0)):
+            model.query(smpl_verts, **data_dict["query_dict"])
         df_pred, _, parts_pred, centers_pred = model.get_preds()
         loss_dict["df_h"] = torch.clamp(df_pred[:, 0:1, :], max=0.1).mean()
         return df_pred, parts_pred, centers_pred
@@ -290,7 +294,8 @@ class ReconFitterBase:
     def compute_smpl_center_pred(self, data_dict, model, smpl):
         with torch.no_grad():
             smpl_verts = smpl()[0]
-            model.query(smpl_verts, **data_dict["query_dict"])
+            with heads(model, _lib.HEAD_CENTERS):
+                model.query(smpl_verts, **data_dict["query_dict"])
             return torch.mean(model.get_preds()[3][:, :3], -1)
 
 
@@ -311,7 +316,8 @@ class ReconFitterBehave(ReconFitterBase):
         loss_dict = {}
         R = self.decopose_axis(obj_R, noise=noise)
         object = self.transform_obj_verts(data_dict["objects"], R, obj_t, obj_s)
-        model.query(object, **data_dict["query_dict"])
+        with heads(model, _lib.HEAD_CENTERS):
+            model.query(object, **data_dict["query_dict"])
         centers_pred_o = model.get_preds()[3]
         obj_center_pred = data_dict["smpl_center"] + torch.mean(centers_pred_o[:, 3:, :], -1)
         self.compute_obj_loss(data_dict, loss_dict, model, obj_s, object)

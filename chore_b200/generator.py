@@ -10,6 +10,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib
+from .net import heads
 
 
 class Generator:
@@ -28,8 +29,11 @@ class Generator:
         """num_steps x { query; t = clamp(df_k, max=thr); t.sum().backward(); p <- p - normalize(grad) * t }"""
         df_idx = 0 if df_type == "human" else 1
         preds = None
-        for _ in range(num_steps):
-            model.query(samples, **query_input)
+        for step in range(num_steps):
+            # only the distance head drives the projection; the other three are needed from the LAST query only
+            # (the reference returns that query's preds), so the earlier steps evaluate one head of four
+            with heads(model, getattr(model, "head_mask", 15) if step == num_steps - 1 else _lib.HEAD_DF):
+                model.query(samples, **query_input)
             preds = model.get_preds()
             df_target = torch.clamp(preds[0][:, df_idx, :], max=self.threshold)
             df_target.sum().backward()

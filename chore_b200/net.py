@@ -53,6 +53,26 @@ class _QueryFn(torch.autograd.Function):
         return g_points, None, None, None, None, None
 
 
+class heads:
+    """`with heads(model, HEAD_DF | HEAD_PARTS): model.query(...)` -- evaluate only the decoder heads a caller
+    reads (the kernel skips the others entirely; their entries of get_preds() are empty placeholders).  A no-op
+    for models without a `head_mask` attribute, e.g. the reference's own CHORE."""
+
+    def __init__(self, model, mask: int):
+        self.model, self.mask = model, mask
+
+    def __enter__(self):
+        self.old = getattr(self.model, "head_mask", None)
+        if self.old is not None:
+            self.model.head_mask = self.mask
+        return self.model
+
+    def __exit__(self, *exc):
+        if self.old is not None:
+            self.model.head_mask = self.old
+        return False
+
+
 class CHORE(nn.Module):
     """Drop-in for model.chore.CHORE at inference / fitting time (chore-release configuration)."""
 

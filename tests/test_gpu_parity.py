@@ -583,3 +583,37 @@ def test_optimize_loops_run_and_descend(net, smpl_layer):
     out = fit.optimize_smpl_object(net, data, obj_iter=2, steps_per_iter=3, log=logs.append)
     assert out[0] is w and len(logs) == 6 and "ocent" in logs[0]
     assert data["smpl_center"].shape == (2, 3) and not torch.equal(data["obj_t"].detach(), t0)
+
+
+def test_head_mask_skips_heads_without_changing_results(net):
+    """A head evaluated alone (the kernel skips the other heads' MMAs, epilogues and weight panels) gives bit-identical
+    values to the same head evaluated with all four; `heads()` scopes the mask for the reference-style callers."""
+    import chore_b200
+    from chore_b200 import _lib
+    from chore_b200.net import heads
+    feat, tmpx = O.synth_features(91, B=2)
+    set_maps(net, feat, tmpx)
+    f, s = net._maps()
+    pts = torch.cat([O.synth_points("frustum", 92, 2, 700), O.synth_points("init_box", 93, 2, 333)], 1).to(DEV)
+    cc = torch.tensor([[1008., 995.], [990., 1001.]], device=DEV)
+    full, _ = net.handle.query_fwd(f, s, pts, cc, 15)
+    for mask in (1, 2, 4, 8, 5, 9, 10, 14):
+        part, _ = net.handle.query_fwd(f, s, pts, cc, mask)
+        for h in range(4):
+            if mask & (1 << h):
+                assert torch.equal(part[h], full[h]), (mask, h)
+            else:
+                assert part[h] is None
+    with pytest.raises(chore_b200.ChoreError):
+        net.handle.query_fwd(f, s, pts, cc, 0)
+    with heads(net, _lib.HEAD_DF):
+        p = pts.clone().requires_grad_(True)
+        net.query(p, crop_center=cc)
+        df, pca, parts, centers = net.get_preds()
+        assert torch.equal(df, full[0]) and parts.numel() == 0 and centers.numel() == 0
+        torch.clamp(df[:, 0], max=2.0).sum().backward()
+    assert net.head_mask == 15
+    p2 = pts.clone().requires_grad_(True)
+    net.query(p2, crop_center=cc)
+    torch.clamp(net.get_preds()[0][:, 0], max=2.0).sum().backward()
+    assert torch.equal(p.grad, p2.grad)
