@@ -24,12 +24,17 @@ class ChoreError(RuntimeError):
     pass
 
 
+class AdamEntry(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("rows", C.c_int), ("cols", C.c_int), ("grad_ld", C.c_int)]
+
+
 class TensorDesc(C.Structure):
     _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("ndim", C.c_int), ("shape", C.c_int64 * 4),
                 ("on_device", C.c_int)]
 
 
-_P, _I, _U32, _I64 = C.c_void_p, C.c_int, C.c_uint32, C.c_int64
+_P, _I, _U32, _I64, _F = C.c_void_p, C.c_int, C.c_uint32, C.c_int64, C.c_float
 # every symbol include/chore_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "chore_create": (_I, [_I, C.POINTER(_P)]),
@@ -51,6 +56,13 @@ SIGNATURES = {
     "chore_landmarks_load": (_I, [_P, _P, _P, _P, _I, _I, _I]),
     "chore_landmarks_fwd": (_I, [_P, _P, _I, _P, _P]),
     "chore_landmarks_bwd": (_I, [_P, _P, _I, _P, _I, _P]),
+    "chore_fit_workspace_floats": (C.c_size_t, [_I, _I]),
+    "chore_fit_smpl_field_grads": (_I, [_P, _P, _P, _P, _I, _I, _F, _F, _P, _P, _P, _P, _P]),
+    "chore_fit_landmark_grads": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _F, _F, C.POINTER(C.c_float), _P, _P, _P]),
+    "chore_fit_pose_prior_grads": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _P, _P, _P, _P]),
+    "chore_fit_obj_field_grads": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P]),
+    "chore_add_rowvec": (_I, [_P, _P, _P, _I, _I, _F, _P]),
+    "chore_adam_step": (_I, [_P, C.POINTER(AdamEntry), _I, _F, _F, _F, _F, _P, _P]),
     "chore_rigid_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P]),
     "chore_rigid_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "chore_project_so3": (_I, [_P, _P, _I, _P, _P]),
@@ -268,6 +280,59 @@ class Handle:
             self._check(self.lib.chore_landmarks_bwd(self.h, g_out.data_ptr(), g_out.shape[0], g_verts.data_ptr(), int(acc),
                                                      _stream()))
         return g_verts
+
+    # ---- fit-step losses / optimiser (csrc/fit_loss.cu) ------------------------------------------
+    def fit_workspace(self, B: int, N: int, device) -> torch.Tensor:
+        return torch.empty(int(self.lib.chore_fit_workspace_floats(B, N)), device=device)
+
+    def fit_smpl_field_grads(self, df, parts, labels, wd: float, wp: float, loss, ws):
+        check_cuda(df, parts, loss, ws)
+        if labels.dtype != torch.int64 or not labels.is_contiguous():
+            raise ChoreError("labels must be a contiguous int64 tensor")
+        B, _, N = df.shape
+        g_df, g_parts = torch.empty_like(df), torch.empty_like(parts)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.chore_fit_smpl_field_grads(self.h, df.data_ptr(), parts.data_ptr(), labels.data_ptr(), B, N, wd, wp,
+                                                            g_df.data_ptr(), g_parts.data_ptr(), loss.data_ptr(), ws.data_ptr(), _stream()))
+        return g_df, g_parts
+
+    def fit_landmark_grads(self, lm, kpts, crop_center, n_joints: int, z0: float, cz: float, cj: float, cam, loss):
+        check_cuda(lm, kpts, crop_center, loss)
+        g_lm = torch.empty_like(lm)
+        cam_c = (C.c_float * 6)(*[float(x) for x in cam])
+        with torch.cuda.device(self.device):
+            self._check(self.lib.chore_fit_landmark_grads(self.h, lm.data_ptr(), _ptr(kpts), crop_center.data_ptr(), lm.shape[0], lm.shape[1],
+                                                          n_joints, z0, cz, cj, cam_c, g_lm.data_ptr(), loss.data_ptr(), _stream()))
+        return g_lm
+
+    def fit_pose_prior_grads(self, pose, pose_init, priors, cb: float, ch: float, cp: float, g_pose, loss, ws) -> None:
+        """priors: (body_mean, body_prec, hand_mean, lhand_prec, rhand_prec) or None; adds into g_pose."""
+        pr = priors if priors is not None else (None,) * 5
+        check_cuda(pose, pose_init, g_pose, loss, ws, *pr)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.chore_fit_pose_prior_grads(self.h, pose.data_ptr(), _ptr(pose_init), *[_ptr(t) for t in pr], pose.shape[0],
+                                                            pose.shape[1], cb, ch, cp, g_pose.data_ptr(), loss.data_ptr(), ws.data_ptr(),
+                                                            _stream()))
+
+    def fit_obj_field_grads(self, obj, df, centers, smpl_center, s, s0: float, wo: float, wc: float, wsc: float, loss, ws):
+        check_cuda(obj, df, centers, smpl_center, s, loss, ws)
+        B, N = obj.shape[0], obj.shape[1]
+        g_df, g_cen = torch.empty_like(df), torch.empty_like(centers)
+        dvec = torch.empty(B, 3, device=obj.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.chore_fit_obj_field_grads(self.h, obj.data_ptr(), df.data_ptr(), centers.data_ptr(), smpl_center.data_ptr(),
+                                                           s.data_ptr(), B, N, s0, wo, wc, wsc, g_df.data_ptr(), g_cen.data_ptr(),
+                                                           dvec.data_ptr(), loss.data_ptr(), ws.data_ptr(), _stream()))
+        return g_df, g_cen, dvec
+
+    def add_rowvec(self, x, v, alpha: float) -> None:
+        check_cuda(x, v)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.chore_add_rowvec(self.h, x.data_ptr(), v.data_ptr(), x.shape[0], x.shape[1], alpha, _stream()))
+
+    def adam_step(self, entries, n: int, lr: float, beta1: float, beta2: float, eps: float, step) -> None:
+        with torch.cuda.device(self.device):
+            self._check(self.lib.chore_adam_step(self.h, entries, n, lr, beta1, beta2, eps, step.data_ptr(), _stream()))
 
     # ---- rigid object ------------------------------------------------------------------------
     def rigid_fwd(self, verts, R, t, s):

@@ -419,17 +419,46 @@ class ReconFitterBehave(ReconFitterBase):
         return smpl, data_dict["obj_R"], data_dict["obj_t"]
 
 
-class FusedFitSteps:
-    """The two inner optimisation steps of the fitting loop with NO autograd graph: explicit forward kernels,
-    closed-form loss gradients (a handful of elementwise torch ops under no_grad) and explicit adjoint kernels,
-    so a step is  LBS -> field query -> dL/d(preds) -> query adjoint -> LBS adjoint -> Adam  (SMPL phase,
-    recon/recon_fit_behave.py:293-337 field terms) or  SO(3) -> rigid -> query -> dL/d(preds) -> query adjoint
-    -> rigid adjoint -> SO(3) adjoint -> Adam  ('object only' phase, recon/recon_fit_behave.py:165-198).
-    Both are plain stream-ordered launches, hence capturable in a CUDA graph (`graphed()`).
+class FusedAdam:
+    """torch.optim.Adam(params, lr, betas, eps) (no weight decay, no amsgrad) as ONE kernel launch per step for up to
+    8 small tensors (chore_adam_step); the step counter lives on the device, so a captured step replays correctly.
+    `grads[i]` is the tensor the gradient of params[i] is read from at step() time: a (rows, cols) view that may be a
+    column slice of a wider, persistent buffer (its storage must not move between steps -- true inside a CUDA graph
+    and for buffers the caller keeps)."""
 
-    The reference queries the object points twice per step (recon_fit_behave.py:179 + recon_fit_base.py:515);
-    the two queries have identical inputs, so one forward + one adjoint launch (heads df and centers) gives the
-    same losses and gradients.  Loss weights / decay are those of get_loss_weights()."""
+    def __init__(self, params, lr=0.006, betas=(0.9, 0.999), eps=1e-8, handle=None):
+        self.params = [p for p in params]
+        assert 0 < len(self.params) <= 8
+        self.lr, self.betas, self.eps = float(lr), betas, float(eps)
+        dev = self.params[0].device
+        self.handle = handle or _lib.get_handle(dev)
+        self.exp_avg = [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in self.params]
+        self.exp_avg_sq = [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in self.params]
+        self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def step(self, grads) -> None:
+        ent = (_lib.AdamEntry * len(self.params))()
+        for e, p, g, m, v in zip(ent, self.params, grads, self.exp_avg, self.exp_avg_sq):
+            p2 = p.detach().view(p.shape[0], -1) if p.dim() > 1 else p.detach().view(1, -1)
+            g2 = g.view(g.shape[0], -1) if g.dim() > 1 else g.view(1, -1)
+            assert p2.is_contiguous() and g2.stride(-1) == 1 and g2.shape == p2.shape and g2.dtype == torch.float32
+            e.param, e.grad, e.exp_avg, e.exp_avg_sq = p2.data_ptr(), g2.data_ptr(), m.data_ptr(), v.data_ptr()
+            e.rows, e.cols, e.grad_ld = p2.shape[0], p2.shape[1], (g2.stride(0) if g2.shape[0] > 1 else p2.shape[1])
+        self.handle.adam_step(ent, len(self.params), self.lr, self.betas[0], self.betas[1], self.eps, self.step_count)
+
+
+class FusedFitSteps:
+    """The two inner optimisation steps of the fitting loop with NO autograd graph and no eager elementwise ops:
+      SMPL phase (recon/recon_fit_behave.py:293-337):   LBS -> landmarks -> field query (df, parts) -> loss kernels
+          (df_h + part CE, smplz + j2d, priors + pinit) -> query adjoint -> landmark adjoint -> LBS adjoint -> Adam
+      'object only' phase (recon/recon_fit_behave.py:165-198):   SO(3) -> rigid -> field query (df, centers) -> loss
+          kernels (object, scale, ocent) -> query adjoint -> rigid adjoint -> SO(3) adjoint -> Adam
+    Every stage is one or two launches of libchore_b200.so (csrc/fit_loss.cu holds the loss / Adam kernels), all
+    stream-ordered, hence capturable in a CUDA graph (`graphed()`).
+
+    The reference queries the object points twice per step (recon_fit_behave.py:179 + recon_fit_base.py:515) with
+    identical inputs, so one forward + one adjoint launch (heads df and centers) gives the same losses and gradients.
+    Loss weights / decay are those of get_loss_weights(); Adam is torch.optim.Adam's update rule (FusedAdam)."""
 
     W = {"object": 30.0 ** 2, "part": 0.05 ** 2, "scale": 10.0 ** 2, "df_h": 30.0 ** 2, "ocent": 15 ** 2, "pinit": 5 ** 2,
          "pose": 1e-5, "hand": 1e-5, "smplz": 30 ** 2, "j2d": 0.3 ** 2}
@@ -444,12 +473,24 @@ class FusedFitSteps:
         self.R, self.t, self.s = obj_R, obj_t, obj_s
         self.obj_scale, self.decay = obj_scale, decay
         self.smpl_params = [smpl.trans, smpl.global_pose, smpl.body_pose, smpl.top_betas, smpl.other_betas]
-        self.opt_smpl = torch.optim.Adam(self.smpl_params, lr_smpl, capturable=True)
-        self.opt_obj = torch.optim.Adam([obj_t, obj_R, obj_s], lr_obj, capturable=True)
         self.h_net = net.handle
         self.h_lbs = smpl.smpl.handle
         self.h_aux = _lib.get_handle(obj_t.device)
+        self.opt_smpl = FusedAdam(self.smpl_params, lr_smpl, handle=self.h_aux)
+        self.opt_obj = FusedAdam([obj_t, obj_R, obj_s], lr_obj, handle=self.h_aux)
         self.cc = data_dict["query_dict"]["crop_center"].detach().float().contiguous()
+        dev = obj_t.device
+        nmax = max(smpl.offsets.shape[1], data_dict["objects"].shape[1]) if "objects" in data_dict else smpl.offsets.shape[1]
+        self.ws = self.h_aux.fit_workspace(obj_t.shape[0], nmax, dev)
+        self.loss_smpl = torch.zeros(1, device=dev)
+        self.loss_obj = torch.zeros(1, device=dev)
+        self.priors_dev = None
+        if fitter is not None and fitter.priors is not None:
+            bp, hp = fitter.priors
+            assert bp.prefix == 3 and bp.end == 66 and hp.prefix == 66, "priors are expected on pose[3:66] and pose[66:]"
+            self.priors_dev = tuple(t.to(dev).float().contiguous() for t in
+                                    (bp.mean.reshape(-1), bp.prec, hp.mean.reshape(-1), hp.lhand_prec[0], hp.rhand_prec[0]))
+        self.pose_init = data_dict["pose_init"].detach().float().contiguous() if "pose_init" in data_dict else None
 
     @torch.no_grad()
     def smpl_step(self):
@@ -458,63 +499,35 @@ class FusedFitSteps:
         pose = torch.cat([sm.global_pose, sm.body_pose, sm.hand_pose], 1)
         betas = torch.cat([sm.top_betas, sm.other_betas], 1)
         trans, off = sm.trans.detach(), sm.offsets.detach()
+        loss = self.loss_smpl.zero_()
         verts, _, _, _ = self.h_lbs.lbs_fwd(pose, betas, trans, off, want_posed=False)
         (df, _, parts, _), _ = self.h_net.query_fwd(feat, skip, verts, self.cc, _lib.HEAD_DF | _lib.HEAD_PARTS)
         B, _, N = df.shape
         k = 1.0 / (1.0 + self.decay)
         # L = w_dfh * mean(min(df_h, 0.1)) + w_part * mean_b sum_n CE(parts, labels)
-        dfh = df[:, 0]
-        logp = torch.log_softmax(parts, 1)
-        labels = d["part_labels"]
-        loss = self.W["df_h"] * k * torch.clamp(dfh, max=0.1).mean() - self.W["part"] * k * logp.gather(1, labels.unsqueeze(1)).sum() / B
-        g_df = torch.zeros_like(df)
-        g_df[:, 0] = (dfh <= 0.1).float() * (self.W["df_h"] * k / (B * N))
-        g_parts = logp.exp()
-        g_parts.scatter_add_(1, labels.unsqueeze(1), torch.full_like(labels, -1, dtype=g_parts.dtype).unsqueeze(1))
-        g_parts *= self.W["part"] * k / B
+        g_df, g_parts = self.h_aux.fit_smpl_field_grads(df, parts, d["part_labels"], self.W["df_h"] * k / (B * N), self.W["part"] * k / B,
+                                                        loss, self.ws)
         g_verts = self.h_net.query_bwd(feat, skip, verts, self.cc, [g_df, None, g_parts, None])
         fit = self.fitter
         if getattr(sm, "regressors", None) is not None and fit is not None:
             # smplz: 30^2 mean_b (J8.z - z0)^2; j2d ('kpts'): 0.3^2 mean_{b,j} conf ||proj(J) - kpts||^2 (recon_fit_base.py:230,653-676)
-            lm = sm.regressors.handle.landmarks_fwd(verts)
-            J = lm[:, :sm.regressors.sizes[0]]
-            g_lm = torch.zeros_like(lm)
-            dz = J[:, 8, 2] - fit.z_0
-            loss = loss + self.W["smplz"] * k * (dz ** 2).mean()
-            g_lm[:, 8, 2] = self.W["smplz"] * k * 2.0 / B * dz
-            if self.phase == "kpts":
-                sc = fit.net_in_size / fit.crop_size
-                x, y, z = J[..., 0], J[..., 1], J[..., 2]
-                px = (fit.fx_px * x / z + fit.cx_px + fit.crop_size / 2 - self.cc[:, 0:1]) * sc
-                py = (fit.fy_px * y / z + fit.cy_px + fit.crop_size / 2 - self.cc[:, 1:2]) * sc
-                kp = d["body_kpts"]
-                ex, ey, conf = px - kp[..., 0], py - kp[..., 1], kp[..., 2]
-                loss = loss + self.W["j2d"] * k * ((ex ** 2 + ey ** 2) * conf).mean()
-                c = self.W["j2d"] * k * 2.0 / (B * J.shape[1]) * conf * sc
-                gx, gy = c * ex * fit.fx_px / z, c * ey * fit.fy_px / z
-                nJ = J.shape[1]
-                g_lm[:, :nJ, 0] += gx
-                g_lm[:, :nJ, 1] += gy
-                g_lm[:, :nJ, 2] += -(gx * x + gy * y) / z
-            sm.regressors.handle.landmarks_bwd(g_lm, g_verts)          # g_verts += R^T g_lm
+            hl = sm.regressors.handle
+            lm = hl.landmarks_fwd(verts)
+            nJ = sm.regressors.sizes[0]
+            kp = d["body_kpts"] if self.phase == "kpts" else None
+            cam = (fit.fx_px, fit.fy_px, fit.cx_px, fit.cy_px, fit.crop_size / 2, fit.net_in_size / fit.crop_size)
+            g_lm = self.h_aux.fit_landmark_grads(lm, kp, self.cc, nJ, fit.z_0, self.W["smplz"] * k / B, self.W["j2d"] * k / (B * nJ), cam, loss)
+            hl.landmarks_bwd(g_lm, g_verts)          # g_verts += R^T g_lm
         g_pose, g_betas, g_trans, _ = self.h_lbs.lbs_bwd(pose, betas, trans, off, g_verts, None, False)
-        if fit is not None and fit.priors is not None:                  # Mahalanobis priors (recon_fit_base.py:522-535)
-            bp, hp = fit.priors
-            tb = (pose[:, bp.prefix:bp.end] - bp.mean) @ bp.prec
-            tl = (pose[:, hp.prefix:hp.prefix + 45] - hp.mean[:, :45]) @ hp.lhand_prec[0]
-            tr = (pose[:, hp.prefix + 45:] - hp.mean[:, 45:]) @ hp.rhand_prec[0]
-            # the hand term is total / 45 (see HandPrior.__call__), the body term a mean over the batch
-            loss = loss + self.W["pose"] * k * (tb ** 2).sum(1).mean() + self.W["hand"] * k * ((tl ** 2).sum() + (tr ** 2).sum()) / 45.0
-            g_pose[:, bp.prefix:bp.end] += self.W["pose"] * k * 2.0 / B * (tb @ bp.prec.t())
-            g_pose[:, hp.prefix:hp.prefix + 45] += self.W["hand"] * k * 2.0 / 45.0 * (tl @ hp.lhand_prec[0].t())
-            g_pose[:, hp.prefix + 45:] += self.W["hand"] * k * 2.0 / 45.0 * (tr @ hp.rhand_prec[0].t())
-        if "pose_init" in d:     # 5^2 * mean_b sum (pose[3:72] - pose_init)^2
-            diff = pose[:, 3:72] - d["pose_init"]
-            loss = loss + self.W["pinit"] * k * (diff ** 2).sum(-1).mean()
-            g_pose[:, 3:72] += self.W["pinit"] * k * 2.0 / B * diff
-        sm.trans.grad, sm.global_pose.grad, sm.body_pose.grad = g_trans, g_pose[:, :3].contiguous(), g_pose[:, 3:66].contiguous()
-        sm.top_betas.grad, sm.other_betas.grad = g_betas[:, :2].contiguous(), g_betas[:, 2:].contiguous()
-        self.opt_smpl.step()
+        if self.priors_dev is not None or self.pose_init is not None:
+            # Mahalanobis priors (recon_fit_base.py:522-535; the hand term is total / 45, see HandPrior.__call__) and
+            # 5^2 * mean_b sum (pose[3:72] - pose_init)^2 (recon_fit_behave.py:317-319)
+            self.h_aux.fit_pose_prior_grads(pose, self.pose_init, self.priors_dev, self.W["pose"] * k / B, self.W["hand"] * k / 45.0,
+                                            self.W["pinit"] * k / B, g_pose, loss, self.ws)
+        self._g_smpl = (g_trans, g_pose[:, :3], g_pose[:, 3:66], g_betas[:, :2], g_betas[:, 2:])
+        for p, g in zip(self.smpl_params, self._g_smpl):
+            p.grad = g
+        self.opt_smpl.step(self._g_smpl)
         return loss
 
     @torch.no_grad()
@@ -525,27 +538,23 @@ class FusedFitSteps:
         B, N, _ = obj0.shape
         if noise is None:
             noise = torch.rand(B, 3, 3, device=obj0.device)
-        rot_in = (self.R + 1e-4 * noise).contiguous()                        # decopose_axis (recon_fit_base.py:373-384)
+        loss = self.loss_obj.zero_()
+        rot_in = torch.add(self.R, noise, alpha=1e-4)                        # decopose_axis (recon_fit_base.py:373-384)
         Rm = self.h_aux.project_so3(rot_in)
         t, s = self.t.detach(), self.s.detach()
         obj = self.h_aux.rigid_fwd(obj0, Rm, t, s)
         (df, _, _, cen), _ = self.h_net.query_fwd(feat, skip, obj, self.cc, _lib.HEAD_DF | _lib.HEAD_CENTERS)
         k = 1.0 / (1.0 + self.decay)
-        dfo = df[:, 1]
-        dvec = obj.mean(1) - d["smpl_center"] - cen[:, 3:].mean(-1)          # (B,3)
-        loss = (self.W["object"] * k * torch.clamp(dfo, max=0.8).mean() + self.W["scale"] * k * ((s - self.obj_scale) ** 2).mean()
-                + self.W["ocent"] * k * (dvec ** 2).sum(-1).mean())
-        g_df = torch.zeros_like(df)
-        g_df[:, 1] = (dfo <= 0.8).float() * (self.W["object"] * k / (B * N))
-        g_cen = torch.zeros_like(cen)
-        coef = self.W["ocent"] * k * 2.0 / (B * N)
-        g_cen[:, 3:] = (-coef * dvec).unsqueeze(-1)
+        wc = self.W["ocent"] * k / B
+        g_df, g_cen, dvec = self.h_aux.fit_obj_field_grads(obj, df, cen, d["smpl_center"], s, self.obj_scale, self.W["object"] * k / (B * N), wc,
+                                                           self.W["scale"] * k / B, loss, self.ws)
         g_obj = self.h_net.query_bwd(feat, skip, obj, self.cc, [g_df, None, None, g_cen])
-        g_obj += (coef * dvec).unsqueeze(1)
+        self.h_aux.add_rowvec(g_obj, dvec, 2.0 * wc / N)
         g_R, g_t, g_s, _ = self.h_aux.rigid_bwd(obj0, Rm, t, s, g_obj, False)
-        g_s += self.W["scale"] * k * 2.0 / B * (s - self.obj_scale)
-        self.R.grad, self.t.grad, self.s.grad = self.h_aux.project_so3_bwd(rot_in, g_R), g_t, g_s
-        self.opt_obj.step()
+        g_s.add_(s - self.obj_scale, alpha=self.W["scale"] * k * 2.0 / B)
+        g_rot = self.h_aux.project_so3_bwd(rot_in, g_R)
+        self.R.grad, self.t.grad, self.s.grad = g_rot, g_t, g_s
+        self.opt_obj.step((g_t, g_rot, g_s))
         return loss
 
     def graphed(self):

@@ -173,6 +173,55 @@ int chore_project_so3(chore_handle *h, const float *mats, int B, float *out, voi
 int chore_project_so3_bwd(chore_handle *h, const float *mats, const float *g_out, int B,
                           float *g_mats, void *stream);
 
+/* ---- fit-step losses and optimiser: the non-field arithmetic of one optimisation step of
+ *      ReconFitterBehave.forward_smpl / forward_step('object only') (recon/recon_fit_behave.py:165-222,
+ *      293-337) with get_loss_weights (:339-358) folded into the coefficients, as closed-form loss
+ *      values + gradients w.r.t. the network outputs / SMPL parameters, and torch.optim.Adam.step.
+ *      All pointers are device pointers; `loss` is ONE device float that every call adds its terms to;
+ *      `workspace` holds chore_fit_workspace_floats(B, N) floats. ------------------------------ */
+size_t chore_fit_workspace_floats(int B, int N);
+/* wd * sum min(df_h, 0.1) + wp * sum CE(parts, labels): df (B,2,N), parts (B,14,N), labels (B,N) int64
+ * -> g_df (B,2,N), g_parts (B,14,N)   (recon_fit_base.py:537-542, recon_fit_behave.py:313) */
+int chore_fit_smpl_field_grads(chore_handle *h, const float *df, const float *parts, const int64_t *labels,
+                               int B, int N, float wd, float wp, float *g_df, float *g_parts, float *loss,
+                               float *workspace, void *stream);
+/* cz * sum_b (J[b,8].z - z0)^2 (+ cj * sum conf |proj(J) - kpts|^2 when body_kpts (B,n_joints,3) is given):
+ * landmarks (B,L,3) -> g_landmarks (B,L,3).  cam = {fx_px, fy_px, cx_px, cy_px, crop_size/2,
+ * net_in_size/crop_size}   (recon_fit_base.py:230-231, 653-676; model/camera.py:51-71) */
+int chore_fit_landmark_grads(chore_handle *h, const float *landmarks, const float *body_kpts,
+                             const float *crop_center, int B, int L, int n_joints, float z0, float cz, float cj,
+                             const float cam[6], float *g_landmarks, float *loss, void *stream);
+/* cb * sum_b |(pose[3:66]-mean) P|^2 + ch * sum_b,hands |(pose[66:]-mean_h) P_h|^2 + cp * sum_b |pose[3:72]-pose_init|^2;
+ * gradients are ADDED to g_pose (B,156).  Priors / pose_init may be NULL (term skipped)
+ * (lib_smpl/th_smpl_prior.py:32-39, lib_smpl/th_hand_prior.py:69-78, recon_fit_behave.py:317-319) */
+int chore_fit_pose_prior_grads(chore_handle *h, const float *pose, const float *pose_init, const float *body_mean,
+                               const float *body_prec, const float *hand_mean, const float *lhand_prec,
+                               const float *rhand_prec, int B, int n_pose, float cb, float ch, float cp, float *g_pose,
+                               float *loss, float *workspace, void *stream);
+/* object step: dvec_b = mean(obj_b) - smpl_center_b - mean(centers_b[3:6]);
+ * loss += wo * sum min(df_o, 0.8) + wc * sum_b |dvec_b|^2 + ws * sum_b (s_b - s0)^2;
+ * g_df (B,2,N), g_centers (B,6,N), dvec (B,3) out   (recon_fit_base.py:513-520, recon_fit_behave.py:175-198) */
+int chore_fit_obj_field_grads(chore_handle *h, const float *obj, const float *df, const float *centers,
+                              const float *smpl_center, const float *s, int B, int N, float s0, float wo, float wc,
+                              float ws, float *g_df, float *g_centers, float *dvec, float *loss, float *workspace,
+                              void *stream);
+/* x (B,N,3) += alpha * v (B,3) broadcast over N */
+int chore_add_rowvec(chore_handle *h, float *x, const float *v, int B, int N, float alpha, void *stream);
+
+/* torch.optim.Adam.step (weight_decay 0, amsgrad off) for up to CHORE_ADAM_MAX_ENTRIES small tensors in one
+ * launch.  `step` is a device int32 step counter (read, then incremented by the kernel: graph-replay safe). */
+#define CHORE_ADAM_MAX_ENTRIES 8
+typedef struct {
+    float *param;            /* (rows, cols) contiguous                                   */
+    const float *grad;       /* (rows, cols) with leading dimension grad_ld (a column slice
+                                of a wider gradient buffer is fine)                       */
+    float *exp_avg;          /* (rows, cols) contiguous state                             */
+    float *exp_avg_sq;
+    int rows, cols, grad_ld;
+} chore_adam_entry;
+int chore_adam_step(chore_handle *h, const chore_adam_entry *entries, int n, float lr, float beta1, float beta2,
+                    float eps, int32_t *step, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
