@@ -192,6 +192,10 @@ class Handle:
             return g_points
         # scratch comes from torch's allocator: stable under CUDA-graph capture (graph-private pool)
         nbytes = int(self.lib.chore_query_bwd_workspace_bytes(B, N))
+        # k x the base size lets the k heads with a gradient run concurrently in ONE launch (latency-bound small queries)
+        k = sum(g is not None for g in grads)
+        if k > 1 and nbytes * k <= (512 << 20):
+            nbytes *= k
         ws = torch.empty(max(nbytes, 4) // 4, dtype=torch.float32, device=points.device)
         with torch.cuda.device(self.device):
             self._check(self.lib.chore_query_bwd_ws(self.h, feat.data_ptr(), skip.data_ptr(), feat.shape[1], feat.shape[2],

@@ -70,10 +70,15 @@ struct TcParams {
     long long tiles_per_b, total_tiles;
     unsigned long long *dbg;          // optional [grid][16] wait-cycle counters (CHORE_B200_TC_TRACE)
     // backward (query_bwd_tc_kernel): one launch per head
-    int bwd_head;                     // head processed by this launch
-    int bwd_accumulate;               // gX += (heads after the first)
-    const float *g_head;              // upstream gradient of this head (B, nout, N)
-    const unsigned char *wstream_bwd; // this head's 40-panel stream
+    // work item = (tile, slot); slot s evaluates head bwd_heads[s] into its own gX buffer (gX + s * gx_slot_stride), so
+    // several heads run concurrently in ONE launch; with a single slot the heads are launched one after the other
+    // and bwd_accumulate adds into the shared buffer
+    int bwd_nslots;
+    int bwd_heads[4];
+    int bwd_accumulate;               // gX += (heads after the first; single-slot mode only)
+    const float *g_heads[4];          // upstream gradient per slot (B, nout, N)
+    const unsigned char *wstream_bwd; // the four per-head 40-panel streams, head-major
+    long long gx_slot_stride;         // floats between the gX buffers of two slots
     float *gX;                        // (B*N, 384) gradient w.r.t. the (permuted) feature column
     float *g_points;                  // geometry kernel output (B, N, 3)
 };
@@ -567,7 +572,8 @@ __global__ void __launch_bounds__(kThreads, 1) query_bwd_tc_kernel(const TcParam
     uint8_t *ringW = ringAct + 2 * (size_t)kStageA;          // [6][16K]
     BarsB *bars = reinterpret_cast<BarsB *>(ringW + (size_t)kBwdNW * kPanelBytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int hd = q.bwd_head;
+    const int nslots = q.bwd_nslots;
+    const long long total_items = q.total_tiles * nslots;      // item = tile * nslots + slot
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
@@ -591,16 +597,18 @@ __global__ void __launch_bounds__(kThreads, 1) query_bwd_tc_kernel(const TcParam
     if (warp == 0) {
         // ---------------- weight producer ----------------
         uint32_t u = 0;
-        for (long long tile = first_tile; tile < q.total_tiles; tile += tile_stride)
+        for (long long item = first_tile; item < total_items; item += tile_stride) {
+            const unsigned char *wsrc = q.wstream_bwd + (size_t)q.bwd_heads[item % nslots] * kBwdUnits * kPanelBytes;
             for (int i = 0; i < kBwdUnits; ++i, ++u) {
                 const int s = u % kBwdNW;
                 mbar_wait(&bars->w_empty[s], ((u / kBwdNW) & 1) ^ 1);
                 if (elect_one()) {
                     mbar_arrive_expect_tx(&bars->w_full[s], kPanelBytes);
-                    bulk_g2s(ringW + (size_t)s * kPanelBytes, q.wstream_bwd + (size_t)i * kPanelBytes, kPanelBytes, &bars->w_full[s]);
+                    bulk_g2s(ringW + (size_t)s * kPanelBytes, wsrc + (size_t)i * kPanelBytes, kPanelBytes, &bars->w_full[s]);
                 }
                 __syncwarp();
             }
+        }
     } else if (warp == 1) {
         // ---------------- MMA issuer ----------------
         constexpr uint32_t idesc = make_idesc(kTileM, 128);
@@ -629,7 +637,7 @@ __global__ void __launch_bounds__(kThreads, 1) query_bwd_tc_kernel(const TcParam
             __syncwarp();
             u += 2;
         };
-        for (long long tile = first_tile; tile < q.total_tiles; tile += tile_stride, ++tile_i) {
+        for (long long item = first_tile; item < total_items; item += tile_stride, ++tile_i) {
             // F1: layer 1 of this head from the gathered feature blocks
             for (int kb = 0; kb < kL1Blocks; ++kb, ++ablk) {
                 const int sa = ablk % 2;
@@ -678,11 +686,12 @@ __global__ void __launch_bounds__(kThreads, 1) query_bwd_tc_kernel(const TcParam
             ++pass;
         }
     } else if (warp < kEpiWarp0) {
-        // ---------------- gather warps (same as the forward kernel, one pass per tile) ----------------
+        // ---------------- gather warps (same as the forward kernel, one pass per work item) ----------------
         const int g = warp - kGatherWarp0;
         const int half = lane >> 4, l16 = lane & 15;
         uint32_t ablk = 0;
-        for (long long tile = first_tile; tile < q.total_tiles; tile += tile_stride) {
+        for (long long item = first_tile; item < total_items; item += tile_stride) {
+            const long long tile = item / nslots;
             const int b = (int)(tile / q.tiles_per_b);
             const long long n0 = (tile % q.tiles_per_b) * kTileM;
             const float ccx = __ldg(q.crop_center + b * 2), ccy = __ldg(q.crop_center + b * 2 + 1);
@@ -719,11 +728,15 @@ __global__ void __launch_bounds__(kThreads, 1) query_bwd_tc_kernel(const TcParam
         const int e = warp - kEpiWarp0;
         const int quarter = warp & 3, colhalf = e >> 2;
         const int row = quarter * 32 + lane;
-        const int nout = head_out_tc(hd);
         uint8_t *hi = ringAct + (size_t)colhalf * kStageA, *lo = hi + kPanelBytes;     // this warp's activation block
         const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + colhalf * 64;
         uint32_t pass = 0;
-        for (long long tile = first_tile; tile < q.total_tiles; tile += tile_stride) {
+        for (long long item = first_tile; item < total_items; item += tile_stride) {
+            const long long tile = item / nslots;
+            const int slot = (int)(item % nslots);
+            const int hd = q.bwd_heads[slot];
+            const int nout = head_out_tc(hd);
+            const float *g_head = q.g_heads[slot];
             const int b = (int)(tile / q.tiles_per_b);
             const long long n = (tile % q.tiles_per_b) * kTileM + row;
             const bool live = n < q.n_count;
@@ -736,7 +749,7 @@ __global__ void __launch_bounds__(kThreads, 1) query_bwd_tc_kernel(const TcParam
                 const bool inimg = (nx >= -1.0f) && (nx <= 1.0f) && (ny >= -1.0f) && (ny <= 1.0f);
                 const bool use = live && !(hd == 0 && !inimg);
 #pragma unroll
-                for (int o = 0; o < 14; ++o) gout[o] = (use && o < nout) ? __ldg(q.g_head + ((size_t)b * nout + o) * q.N + q.n_start + n) : 0.f;
+                for (int o = 0; o < 14; ++o) gout[o] = (use && o < nout) ? __ldg(g_head + ((size_t)b * nout + o) * q.N + q.n_start + n) : 0.f;
             }
             uint32_t mask[3][2];
             // ---- forward recompute: F1, F2, F3 ----
@@ -815,7 +828,7 @@ __global__ void __launch_bounds__(kThreads, 1) query_bwd_tc_kernel(const TcParam
             // ---- B1 result: accumulator regions 1..3 -> gX[point][384] ----
             mbar_wait(&bars->tm_full, 5 & 1);
             tc_fence_after();
-            float *gx = q.gX + ((size_t)b * q.N + q.n_start + (live ? n : 0)) * kGXLd + colhalf * 64;
+            float *gx = q.gX + (size_t)slot * q.gx_slot_stride + ((size_t)b * q.N + q.n_start + (live ? n : 0)) * kGXLd + colhalf * 64;
 #pragma unroll 1
             for (int reg = 0; reg < 3; ++reg) {
 #pragma unroll
@@ -882,7 +895,11 @@ __global__ void __launch_bounds__(256) query_bwd_geom_kernel(const TcParams q) {
                     const bool ok = ((k & 1) ? xr : xl) && ((k >> 1) ? yb : yt);
                     v[k] = ok ? __ldg(reinterpret_cast<const float2 *>(M + ((size_t)(y0 + (k >> 1)) * W + (x0 + (k & 1))) * C + c)) : make_float2(0.f, 0.f);
                 }
-                const float2 g = __ldg(reinterpret_cast<const float2 *>(gx + (map == 0 ? 0 : 256) + c));
+                float2 g = __ldg(reinterpret_cast<const float2 *>(gx + (map == 0 ? 0 : 256) + c));
+                for (int sl = 1; sl < q.bwd_nslots; ++sl) {      // heads evaluated concurrently: sum their buffers in slot order
+                    const float2 g2 = __ldg(reinterpret_cast<const float2 *>(gx + (size_t)sl * q.gx_slot_stride + (map == 0 ? 0 : 256) + c));
+                    g.x += g2.x; g.y += g2.y;
+                }
                 gix += g.x * (s * (v[1].x - v[0].x) + nn * (v[3].x - v[2].x)) + g.y * (s * (v[1].y - v[0].y) + nn * (v[3].y - v[2].y));
                 giy += g.x * (e * (v[2].x - v[0].x) + w * (v[3].x - v[1].x)) + g.y * (e * (v[2].y - v[0].y) + w * (v[3].y - v[1].y));
             }
@@ -896,9 +913,14 @@ __global__ void __launch_bounds__(256) query_bwd_geom_kernel(const TcParams q) {
         const float gpx = (gnx / 1200.0f) * 2.0f, gpy = (gny / 1200.0f) * 2.0f;
         const float ux = kFx * x, uy = kFy * y;
         float *d = q.g_points + ((size_t)b * q.N + q.n_start + n) * 3;
-        d[0] = kFx * (gpx / z) + gx[320];
-        d[1] = kFy * (gpy / z) + gx[321];
-        d[2] = -gpx * ((ux / z) / z) - gpy * ((uy / z) / z) + gx[322];
+        float g320 = gx[320], g321 = gx[321], g322 = gx[322];
+        for (int sl = 1; sl < q.bwd_nslots; ++sl) {
+            const float *g2 = gx + (size_t)sl * q.gx_slot_stride;
+            g320 += g2[320]; g321 += g2[321]; g322 += g2[322];
+        }
+        d[0] = kFx * (gpx / z) + g320;
+        d[1] = kFy * (gpy / z) + g321;
+        d[2] = -gpx * ((ux / z) / z) - gpy * ((uy / z) / z) + g322;
     }
 }
 
@@ -1026,36 +1048,52 @@ int query_bwd_tc_launch(chore_handle *h, const float *feat, const float *skip, i
     q.total_tiles = q.tiles_per_b * B;
     q.g_points = g_points;
     const size_t need = (size_t)B * N * kGXLd * sizeof(float);
+    int heads[4], nheads = 0;
+    for (int hd = 0; hd < 4; ++hd)
+        if (g_heads[hd]) heads[nheads++] = hd;
+    if (nheads == 0) {
+        CHORE_CUDA(cudaMemsetAsync(g_points, 0, (size_t)B * N * 3 * sizeof(float), st));
+        return CHORE_OK;
+    }
+    // one gX buffer per head => all heads in ONE launch (small problems are latency bound: a fit step has 54..157 tiles
+    // and two heads); falls back to one launch per head accumulating into a single buffer when the scratch is too small
+    int nslots = 1;
     if (workspace != nullptr) {
         // caller-owned scratch (stable under CUDA-graph capture: the pointer is baked into the graph)
         CHORE_CHECK(workspace_bytes >= need, "query backward workspace too small: %zu < %zu bytes", workspace_bytes, need);
         q.gX = static_cast<float *>(workspace);
+        if (workspace_bytes >= need * nheads) nslots = nheads;
     } else {
-        if (h->bwd_ws_bytes < need) {
+        const size_t want = need * nheads <= ((size_t)512 << 20) ? need * nheads : need;
+        if (h->bwd_ws_bytes < want) {
             if (h->bwd_ws) CHORE_CUDA(cudaFree(h->bwd_ws));
             h->bwd_ws = nullptr; h->bwd_ws_bytes = 0;
-            CHORE_CUDA(cudaMalloc(&h->bwd_ws, need));
-            h->bwd_ws_bytes = need;
+            CHORE_CUDA(cudaMalloc(&h->bwd_ws, want));
+            h->bwd_ws_bytes = want;
         }
         q.gX = static_cast<float *>(h->bwd_ws);
+        if (h->bwd_ws_bytes >= need * nheads) nslots = nheads;
     }
+    q.gx_slot_stride = (long long)B * N * kGXLd;
+    q.wstream_bwd = m.wstream_bwd;
     static bool configured = false;
     if (!configured) {
         CHORE_CUDA(cudaFuncSetAttribute(query_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemBytes));
         configured = true;
     }
-    const long long grid = q.total_tiles < h->sm_count ? q.total_tiles : h->sm_count;
-    int launched = 0;
-    for (int hd = 0; hd < 4; ++hd) {
-        if (!g_heads[hd]) continue;
-        q.bwd_head = hd; q.bwd_accumulate = launched > 0; q.g_head = g_heads[hd];
-        q.wstream_bwd = m.wstream_bwd + (size_t)hd * kBwdUnits * kPanelBytes;
+    if (nslots > 1) {
+        q.bwd_nslots = nslots; q.bwd_accumulate = 0;
+        for (int i = 0; i < nslots; ++i) { q.bwd_heads[i] = heads[i]; q.g_heads[i] = g_heads[heads[i]]; }
+        const long long items = q.total_tiles * nslots;
+        const long long grid = items < h->sm_count ? items : h->sm_count;
         CHORE_LAUNCH(query_bwd_tc_kernel, (unsigned)grid, kThreads, kBwdSmemBytes, st, q);
-        ++launched;
-    }
-    if (launched == 0) {
-        CHORE_CUDA(cudaMemsetAsync(g_points, 0, (size_t)B * N * 3 * sizeof(float), st));
-        return CHORE_OK;
+    } else {
+        const long long grid = q.total_tiles < h->sm_count ? q.total_tiles : h->sm_count;
+        q.bwd_nslots = 1;
+        for (int i = 0; i < nheads; ++i) {
+            q.bwd_heads[0] = heads[i]; q.g_heads[0] = g_heads[heads[i]]; q.bwd_accumulate = i > 0;
+            CHORE_LAUNCH(query_bwd_tc_kernel, (unsigned)grid, kThreads, kBwdSmemBytes, st, q);
+        }
     }
     const long long pts = (long long)B * N;
     CHORE_LAUNCH(query_bwd_geom_kernel, (unsigned)((pts + 7) / 8), 256, 0, st, q);

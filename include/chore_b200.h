@@ -106,7 +106,10 @@ int chore_query_bwd(chore_handle *h, const float *feat, const float *skip, int f
                     const float *g_centers, float *g_points, void *stream);
 
 /* Same with caller-owned scratch of chore_query_bwd_workspace_bytes(B, N) bytes (may be 0): required when the
- * call is captured in a CUDA graph, because the scratch pointer is baked into the captured launches. */
+ * call is captured in a CUDA graph, because the scratch pointer is baked into the captured launches.  A scratch of
+ * k times that size lets the k heads with a non-NULL gradient be evaluated concurrently in ONE launch (each head
+ * writes its own buffer, summed in head order afterwards: deterministic); with less, the heads run one after the
+ * other.  Small queries (a fit step: 54..157 tiles, two heads) are latency bound and gain ~1.3x from this. */
 size_t chore_query_bwd_workspace_bytes(int B, int N);
 int chore_query_bwd_ws(chore_handle *h, const float *feat, const float *skip, int fh, int fw,
                        const float *points, const float *crop_center, int B, int N,

@@ -617,3 +617,36 @@ def test_head_mask_skips_heads_without_changing_results(net):
     net.query(p2, crop_center=cc)
     torch.clamp(net.get_preds()[0][:, 0], max=2.0).sum().backward()
     assert torch.equal(p.grad, p2.grad)
+
+
+def test_query_bwd_concurrent_heads_equal_sequential(net):
+    """chore_query_bwd_ws: with scratch for k heads the heads run in one launch (own gX buffer each, summed in head order);
+    with the base scratch they run one after the other, accumulating.  Same summation order => identical bits."""
+    from chore_b200 import _lib
+    feat, tmpx = O.synth_features(95, B=1)
+    set_maps(net, feat, tmpx)
+    f, s = net._maps()
+    N = 1500
+    pts = O.synth_points("frustum", 96, 1, N).to(DEV)
+    cc = torch.tensor([[1008., 995.]], device=DEV)
+    gen = torch.Generator().manual_seed(97)
+    grads = [torch.randn(1, c, N, generator=gen).to(DEV) for c in (2, 9, 14, 6)]
+    h = net.handle
+    base = int(h.lib.chore_query_bwd_workspace_bytes(1, N))
+    assert base == N * 384 * 4
+
+    def run(ws_bytes, gs):
+        ws = torch.empty(ws_bytes // 4, device=DEV)
+        out = torch.empty(1, N, 3, device=DEV)
+        rc = h.lib.chore_query_bwd_ws(h.h, f.data_ptr(), s.data_ptr(), f.shape[1], f.shape[2], pts.data_ptr(), cc.data_ptr(), 1, N,
+                                      *[None if g is None else g.data_ptr() for g in gs], out.data_ptr(), ws.data_ptr(), ws_bytes,
+                                      torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, h.lib.chore_last_error()
+        torch.cuda.synchronize()
+        return out
+
+    for gs in (grads, [grads[0], None, grads[2], None], [None, None, None, grads[3]]):
+        k = sum(g is not None for g in gs)
+        seq, con = run(base, gs), run(base * k, gs)
+        assert torch.isfinite(seq).all() and seq.abs().max() > 0
+        assert torch.equal(seq, con), (k, (seq - con).abs().max().item())
