@@ -150,32 +150,14 @@ def run_reference(args, rank):
 # =====================================================================================================
 # own arm
 # =====================================================================================================
-def fit_iteration_bench(net, dev, iters=100):
-    """fit-iters/sec (BASELINE configs[2] shape): one iteration = SMPL-phase step (LBS -> query 6890 verts ->
-    df_h + part CE -> adjoints -> Adam) + object-phase step (SO(3) -> rigid 20k samples -> query -> losses ->
-    adjoints -> Adam).  Headline: FusedFitSteps replayed from CUDA graphs (no autograd graph, no host sync);
-    beside it the same step through the autograd-Function path (drop-in for the reference's loop)."""
-    import chore_b200
-    from oracle import chore_oracle as O
-    layer = chore_b200.SMPLHLayer(O.make_smplh_buffers(0), device=dev)
-    g = torch.Generator().manual_seed(7)
-
-    def make_state():
-        smpl = chore_b200.SMPLPyTorchWrapperBatch(layer, 1, betas=0.3 * torch.randn(1, 10, generator=torch.Generator().manual_seed(1)),
-                                                  pose=0.1 * torch.randn(1, 156, generator=torch.Generator().manual_seed(2)),
-                                                  trans=torch.tensor([[0.0, 0.1, 2.2]]), device=dev)
-        split = chore_b200.SMPLPyTorchWrapperBatchSplitParams.from_smpl(smpl)
-        R = (torch.eye(3).unsqueeze(0) + 0.05 * torch.randn(1, 3, 3, generator=torch.Generator().manual_seed(3))).to(dev).requires_grad_(True)
-        t = torch.tensor([[0.2, 0.1, 2.3]], device=dev, requires_grad=True)
-        s = torch.ones(1, device=dev, requires_grad=True)
-        return split, R, t, s
-
-    fit = chore_b200.ReconFitterBehave(device=dev)
-    cc = torch.tensor([[1008., 995.]], device=dev)
-    labels = torch.randint(14, (1, 6890), generator=g).to(dev)
-    obj = (0.2 * torch.randn(1, 20000, 3, generator=g)).to(dev)
-    data = {"net": net, "query_dict": {"crop_center": cc}, "part_labels": labels, "objects": obj,
-            "smpl_center": torch.tensor([[0.0, 0.1, 2.2]], device=dev)}
+def fit_iteration_bench(net, dev, iters=300):
+    """fit-iters/sec (BASELINE configs[2] shape): one iteration = SMPL-phase step (LBS -> landmarks -> query 6890 verts ->
+    every forward_smpl term of phase 'kpts': df_h, pose/hand priors, part CE, smplz, pinit, j2d -> adjoints -> Adam) +
+    'object only' step (SO(3) -> rigid 20k samples -> query -> object/scale/ocent -> adjoints -> Adam).
+    Headline: FusedFitSteps replayed from CUDA graphs (no autograd graph, no host sync); beside it the same step through
+    the autograd-Function path (what an unmodified reference loop drives: forward_smpl / forward_step + backward)."""
+    from bench_fit import make_fit_problem
+    fit, cc, build_state = make_fit_problem(net, dev, 1, 20000, seed=7)
 
     def timed(fn, n):
         for _ in range(5):
@@ -189,11 +171,12 @@ def fit_iteration_bench(net, dev, iters=100):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n
 
-    split, R, t, s = make_state()
-    g_smpl, g_obj = chore_b200.FusedFitSteps(net, split, data, R, t, s).graphed()
+    split, (R, t, s), fused = build_state()
+    g_smpl, g_obj = fused.graphed()
     ms_graph = timed(lambda: (g_smpl(), g_obj()), iters)
-    # the autograd-Function path (what an unmodified reference loop would drive)
-    split, R, t, s = make_state()
+    # the autograd-Function path
+    split, (R, t, s), fused = build_state()
+    data = fused.data
     opt_s = torch.optim.Adam([split.trans, split.global_pose, split.body_pose, split.top_betas, split.other_betas], 0.006)
     opt_o = torch.optim.Adam([t, R, s], lr=0.006)
     w = fit.get_loss_weights()
@@ -201,17 +184,18 @@ def fit_iteration_bench(net, dev, iters=100):
 
     def one():
         opt_s.zero_grad()
-        fit.sum_dict(fit.forward_smpl(split, data), w, 1).backward()
+        fit.sum_dict(fit.forward_smpl(split, data, "kpts"), w, 1).backward()
         opt_s.step()
         opt_o.zero_grad()
         fit.sum_dict(fit.forward_step(net, split, data, R, t, s, "object only", noise=noise), w, 1).backward()
         opt_o.step()
 
-    ms_eager = timed(one, max(10, iters // 4))
+    ms_eager = timed(one, max(10, iters // 6))
     return {"fit_iters_per_sec": 1e3 / ms_graph, "ms_per_iter": ms_graph, "iters": iters,
             "autograd_path_iters_per_sec": 1e3 / ms_eager,
-            "iteration": "SMPL-H step (LBS + query 6890 verts, df_h + part CE) + object step (SO3 + rigid 20k pts + query, "
-                         "object/scale/ocent), Adam, B=1; fused adjoint kernels replayed from CUDA graphs"}
+            "iteration": "SMPL-H step (LBS + landmarks + query 6890 verts; df_h, pose/hand priors, part CE, smplz, pinit, j2d) + "
+                         "object-only step (SO3 + rigid 20k pts + query; object/scale/ocent), Adam, B=1; fused loss/adjoint/Adam "
+                         "kernels replayed from CUDA graphs"}
 
 
 def run_ours(args, rank, world, local_rank):

@@ -26,6 +26,46 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
+def make_fit_problem(net, dev, B, n_obj, seed=100):
+    """Synthetic fitting problem with the true shapes: SMPL-H-shaped body model, landmark
+    regressors (137 x 6890, ~270 non-zeros per row), Mahalanobis priors, part labels, 2-D keypoints, `n_obj` object
+    samples per image.  Returns (fitter, crop_center, build_state) where build_state() makes fresh parameters and a
+    FusedFitSteps over them (phase 'kpts': every forward_smpl term)."""
+    import scipy.sparse as sp
+    import chore_b200
+    from chore_b200.fitter import HandPrior, MahalanobisPrior
+    from oracle import chore_oracle as O          # input synthesis only
+    dev = torch.device(dev)
+    layer = chore_b200.SMPLHLayer(O.make_smplh_buffers(0), device=str(dev))
+    g = torch.Generator().manual_seed(seed)
+    regs = [sp.random(L, 6890, density=270 / 6890, format="csr", random_state=7 + i, dtype="float32") for i, L in enumerate((25, 70, 42))]
+    mk_prec = lambda n: torch.tril(0.3 * torch.randn(n, n, generator=g)) + torch.eye(n)
+    fit = chore_b200.ReconFitterBehave(device=str(dev), strict=True, priors=(
+        MahalanobisPrior(0.1 * torch.randn(63, generator=g), mk_prec(63), device=str(dev)),
+        HandPrior(0.1 * torch.randn(90, generator=g), mk_prec(45), mk_prec(45), device=str(dev))))
+    cc = torch.tensor([[1008., 995.]], device=dev).repeat(B, 1)
+    labels = torch.randint(14, (B, 6890), generator=g).to(dev)
+    obj0 = (0.2 * torch.randn(B, n_obj, 3, generator=g)).to(dev)
+    pose0 = 0.1 * torch.randn(B, 156, generator=g)
+    kpts = torch.cat([512 * torch.rand(B, 25, 2, generator=g), torch.rand(B, 25, 1, generator=g)], -1).to(dev)
+    data = {"net": net, "query_dict": {"crop_center": cc}, "part_labels": labels, "objects": obj0,
+            "pose_init": pose0[:, 3:72].to(dev), "body_kpts": kpts,
+            "smpl_center": torch.tensor([[0.0, 0.1, 2.2]], device=dev).repeat(B, 1)}
+
+    def build_state():
+        smpl = chore_b200.SMPLPyTorchWrapperBatch(layer, B, betas=0.3 * torch.randn(B, 10, generator=g), pose=pose0.clone(),
+                                                  trans=torch.tensor([[0.0, 0.1, 2.2]]).repeat(B, 1), device=str(dev), regressors=regs)
+        split = fit.split_smpl(smpl)
+        R = (torch.eye(3).repeat(B, 1, 1) + 0.05 * torch.randn(B, 3, 3, generator=g)).to(dev).requires_grad_(True)
+        t = torch.tensor([[0.2, 0.1, 2.3]], device=dev).repeat(B, 1).requires_grad_(True)
+        s = torch.ones(B, device=dev, requires_grad=True)
+        fused = chore_b200.FusedFitSteps(net, split, data, R, t, s, fitter=fit, phase="kpts")
+        fused.data = data
+        return split, (R, t, s), fused
+
+    return fit, cc, build_state
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=1, help="images in total (sharded over the ranks)")
@@ -42,7 +82,6 @@ def main():
     import torch.distributed as dist
     import chore_b200
     from chore_b200 import dist as cdist
-    from chore_b200.fitter import HandPrior, MahalanobisPrior
     from oracle import chore_oracle as O          # input / weight synthesis only
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
@@ -53,34 +92,12 @@ def main():
     assert B > 0, "more ranks than images"
     net = chore_b200.CHORE(device=str(dev))
     net.load_state_dict(O.make_state_dict(0, "unit"))
-    layer = chore_b200.SMPLHLayer(O.make_smplh_buffers(0), device=str(dev))
-    g = torch.Generator().manual_seed(100 + rank)
-    # synthetic stand-ins with the true shapes: landmark regressors (137 x 6890, ~270 nnz per row), priors
-    import scipy.sparse as sp
-    regs = [sp.random(L, 6890, density=270 / 6890, format="csr", random_state=7 + i, dtype="float32") for i, L in enumerate((25, 70, 42))]
-    mk_prec = lambda n: torch.tril(0.3 * torch.randn(n, n, generator=g)) + torch.eye(n)
-    fit = chore_b200.ReconFitterBehave(device=str(dev), strict=True, priors=(
-        MahalanobisPrior(0.1 * torch.randn(63, generator=g), mk_prec(63), device=str(dev)),
-        HandPrior(0.1 * torch.randn(90, generator=g), mk_prec(45), mk_prec(45), device=str(dev))))
     img_host = torch.cat([O.synth_images(1000 + i, B=1, size=512) for i in mine]).pin_memory()
-    cc = torch.tensor([[1008., 995.]], device=dev).repeat(B, 1)
     pts = O.synth_points("init_box", 5 + rank, B, args.points).to(dev)
-    labels = torch.randint(14, (B, 6890), generator=g).to(dev)
-    obj0 = (0.2 * torch.randn(B, args.points, 3, generator=g)).to(dev)
-    pose0 = 0.1 * torch.randn(B, 156, generator=g)
-    kpts = torch.cat([512 * torch.rand(B, 25, 2, generator=g), torch.rand(B, 25, 1, generator=g)], -1).to(dev)
+    fit, cc, build_state = make_fit_problem(net, dev, B, args.points, seed=100 + rank)
 
     def build():
-        smpl = chore_b200.SMPLPyTorchWrapperBatch(layer, B, betas=0.3 * torch.randn(B, 10, generator=g), pose=pose0.clone(),
-                                                  trans=torch.tensor([[0.0, 0.1, 2.2]]).repeat(B, 1), device=str(dev), regressors=regs)
-        split = fit.split_smpl(smpl)
-        R = (torch.eye(3).repeat(B, 1, 1) + 0.05 * torch.randn(B, 3, 3, generator=g)).to(dev).requires_grad_(True)
-        t = torch.tensor([[0.2, 0.1, 2.3]], device=dev).repeat(B, 1).requires_grad_(True)
-        s = torch.ones(B, device=dev, requires_grad=True)
-        data = {"net": net, "query_dict": {"crop_center": cc}, "part_labels": labels, "objects": obj0,
-                "pose_init": pose0[:, 3:72].to(dev), "body_kpts": kpts,
-                "smpl_center": torch.tensor([[0.0, 0.1, 2.2]], device=dev).repeat(B, 1)}
-        fused = chore_b200.FusedFitSteps(net, split, data, R, t, s, fitter=fit, phase="kpts")
+        split, (R, t, s), fused = build_state()
         return split, (R, t, s), ((fused.smpl_step, fused.object_step) if args.no_graph else fused.graphed())
 
     def job(state):
