@@ -66,6 +66,45 @@ def make_fit_problem(net, dev, B, n_obj, seed=100):
     return fit, cc, build_state
 
 
+def bench_gen(net, dev, img_host, args):
+    """Generator.gen_pc_batch for 'human' and 'object' (recon/generator.py:96-121): init 30 k samples, then outer
+    iterations of {10 projection steps (query df + gradient to the points), surface filter, resample 20 k}.  With random
+    weights the field is not a distance field, so the 4 mm filter is opened up (every sample passes) and the target
+    count fixes the number of outer iterations at 4 per field = 80 forward + 80 backward queries of 20-30 k points."""
+    import chore_b200
+    B = img_host.shape[0]
+    gen = chore_b200.Generator(net, filter_val=1e9, device=str(dev))
+    cc = torch.tensor([[1008., 995.]], device=dev).repeat(B, 1)
+    net.filter(img_host.to(dev))
+
+    def job():
+        out = {}
+        for t in ("human", "object"):
+            init = gen.init_samples(30000, batch_size=B)
+            out[t] = gen.gen_pc_batch(net, t, init, 3 * args.points, {"crop_center": cc}, num_steps=10, sample_num=args.points)
+        return out
+
+    times = []
+    for rep in range(args.reps + 1):
+        torch.manual_seed(rep)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = job()
+        b.record()
+        torch.cuda.synchronize()
+        if rep > 0:
+            times.append(a.elapsed_time(b))
+    n = out["human"]["points"].shape[1]
+    ms = sorted(times)[len(times) // 2]
+    print(json.dumps({"metric": "gen_pc_batch_ms", "value": ms, "unit": "ms per image batch (human + object fields)", "batch": B,
+                      "points_returned_per_field": n, "outer_iterations_per_field": 4, "projection_steps": 10,
+                      "queries": "80 x (df forward + gradient to the points) of 20-30k points + 8 x all-head forward",
+                      "higher_is_better": False, "data": "synthetic", "dtype": "f32",
+                      "note": "reference on CPU: 1.44 s per forward+backward at 20 k points (SURVEY.md section 6) => ~2 min for the same loop"}),
+          flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=1, help="images in total (sharded over the ranks)")
@@ -73,6 +112,7 @@ def main():
     ap.add_argument("--points", type=int, default=20000)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--no-graph", action="store_true", help="launch the fused steps directly (for ncu launch lists)")
+    ap.add_argument("--gen", action="store_true", help="time Generator.gen_pc_batch (neural point cloud stage) instead of the fit loop")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -94,6 +134,8 @@ def main():
     net.load_state_dict(O.make_state_dict(0, "unit"))
     img_host = torch.cat([O.synth_images(1000 + i, B=1, size=512) for i in mine]).pin_memory()
     pts = O.synth_points("init_box", 5 + rank, B, args.points).to(dev)
+    if args.gen:
+        return bench_gen(net, dev, img_host, args)
     fit, cc, build_state = make_fit_problem(net, dev, B, args.points, seed=100 + rank)
 
     def build():

@@ -23,6 +23,7 @@ Reference entry points exercised (paths relative to /root/reference):
   recon/recon_fit_behave.py:293-337          forward_smpl(phase='kpts'), with compute_prior_loss / smplz_loss /
                                              compute_kpts_loss (recon_fit_base.py:230-231,522-535,653-676),
                                              get_landmarks (lib_smpl/wrapper_pytorch.py:176-190)
+  recon/generator.py:123-217,275-282         Generator.gen_pc_batch / compose_outdict / init_samples (closed-form field)
 """
 from __future__ import annotations
 
@@ -266,6 +267,26 @@ def gold_fit_smpl_full(net):
          **{f"prior_{k}": v for k, v in pri.items()})
 
 
+def gold_gen_pc_batch():
+    """Generator.gen_pc_batch + compose_outdict (recon/generator.py:123-217) of the REFERENCE, driven by the
+    closed-form field of oracle/analytic_field.py on the CPU: surface filter, CPU-generator index resampling,
+    min-count truncation, argmax / mean reductions."""
+    from .analytic_field import AnalyticField
+    Generator = ref_shim.load_generator_class()
+    gen = object.__new__(Generator)
+    gen.threshold, gen.filter_val, gen.device = 2.0, 0.004, "cpu"
+    out = {}
+    for df_type, seed in (("human", 71), ("object", 72)):
+        torch.manual_seed(seed)
+        init = gen.init_samples(3000, batch_size=2)
+        init[1] = init[0].flip(0)                        # the reference rescales batch element 0 only (kept quirk)
+        res = gen.gen_pc_batch(AnalyticField(), df_type, init, 25000, {"crop_center": torch.tensor([[1008., 995.]] * 2)}, 10, mute=True)
+        out[f"{df_type}_init"] = init
+        for k, v in res.items():
+            out[f"{df_type}_{k}"] = v
+    save("gen_pc_batch.npz", seed_human=71, seed_object=72, num_points=25000, num_steps=10, **out)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
@@ -279,6 +300,7 @@ def main():
         gold_lbs()
         gold_rigid_and_fit(net)
         gold_fit_smpl_full(net)
+        gold_gen_pc_batch()
 
 
 if __name__ == "__main__":
