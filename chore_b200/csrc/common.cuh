@@ -140,6 +140,12 @@ int query_bwd_tc_launch(chore_handle *h, const float *feat, const float *skip, i
                         const float *crop_center, int B, long long N, const float *const g_heads[4], float *g_points,
                         void *workspace, size_t workspace_bytes, cudaStream_t st);
 bool query_use_tensor_cores();   // CHORE_B200_QUERY=simt selects the fp32 SIMT kernel
+// cta_group::2 forward for all four heads (query_tc2.cu); experimental, opt-in with CHORE_B200_QUERY_2CTA=1
+bool query_tc2_enabled();
+int query_tc2_launch(chore_handle *h, const float *feat, const float *skip, int fh, int fw, const float *points,
+                     const float *crop_center, int B, long long N, long long n_start, long long n_count, int grid_mode,
+                     int batch_index, const int *res, const double *step, const double *bmin, float *const outs[4],
+                     unsigned char *in_img, cudaStream_t st);
 
 // tensor-core encoder convolutions (conv_tc.cu)
 struct ConvTcArgs {

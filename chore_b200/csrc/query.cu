@@ -658,6 +658,8 @@ extern "C" int chore_query_fwd(chore_handle *h, const float *feat, const float *
     q.in_img = in_img;
     fill_weights(q, h->mlp);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (query_use_tensor_cores() && head_mask == CHORE_HEAD_ALL && query_tc2_enabled())     // all heads: CTA-pair kernel
+        return query_tc2_launch(h, feat, skip, fh, fw, points, crop_center, B, N, 0, N, 0, 0, nullptr, nullptr, nullptr, outs, in_img, st);
     if (query_use_tensor_cores())
         return query_tc_launch(h, feat, skip, fh, fw, points, crop_center, B, N, 0, N, 0, 0, nullptr, nullptr, nullptr,
                                head_mask, outs, in_img, st);
@@ -698,6 +700,9 @@ extern "C" int chore_query_grid(chore_handle *h, const float *feat, const float 
     for (int i = 0; i < kNumHeads; ++i) q.out[i] = outs[i] ? outs[i] - (size_t)b * kHeadOut[i] * total : nullptr;
     q.in_img = nullptr;
     fill_weights(q, h->mlp);
+    if (query_use_tensor_cores() && head_mask == CHORE_HEAD_ALL && query_tc2_enabled())
+        return query_tc2_launch(h, feat, skip, fh, fw, nullptr, crop_center, 1, total, start, count, 1, b, res, q.step, q.bmin, q.out, nullptr,
+                                static_cast<cudaStream_t>(stream));
     if (query_use_tensor_cores())
         return query_tc_launch(h, feat, skip, fh, fw, nullptr, crop_center, 1, total, start, count, 1, b, res, q.step, q.bmin,
                                head_mask, q.out, nullptr, static_cast<cudaStream_t>(stream));

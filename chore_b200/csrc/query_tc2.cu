@@ -1,0 +1,504 @@
+// Fused point query on CTA PAIRS (tcgen05 cta_group::2), forward, all four heads.
+//
+// Same contract and arithmetic as query_tc_kernel (query_tc.cu) -- projection, two bilinear gathers, 4-head MLP with
+// the 3-term fp16 split, OUT_DIST mask, reference output layouts -- but two CTAs of a cluster (the two SMs of a TPC)
+// work on two 128-point tiles in lockstep and ONE elected thread of the leader CTA issues M = 256 MMAs for both:
+//
+//   * the B operand (weights) of an MMA is split between the two CTAs' shared memories, so every weight byte is
+//     fetched from L2 once per 256 points and occupies half the ring space per point: the same 4 x 16 KB ring now
+//     holds 2 layer-1 steps of N = 256 (two heads per instruction: CTA r holds the panel of head 2p + r) or
+//     4 layer-2/3 steps (CTA r holds output rows 64r .. 64r+63 of the hi and lo panels in one slot);
+//   * layer 1 runs as N = 256 instructions (161 cycles for two heads instead of 2 x 97, profiles/mma_microbench_r1.txt);
+//   * one issuing thread feeds both tensor pipes.
+//
+// Roles per CTA (14 warps): warp 0 weight producer (its half of every panel), warp 1 MMA issuer in the leader /
+// weight-arrival relay in the peer, warps 2-5 gather, warps 6-13 epilogue.  Producer -> consumer barriers that the
+// issuer waits on (a_full, act_full, tm_empty, w_peer) live in the LEADER's shared memory and are arrived on remotely
+// by the peer; consumer -> producer barriers (a_empty, w_empty, act_empty, tm_full) are local to each CTA and are
+// signalled in both by a multicast tcgen05.commit.
+#include "query_tc_shared.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+
+namespace {
+
+constexpr int kSlotsPerPair = kL1Blocks * 2 * 2 + 2 * 4 * 2 + 4;     // 24 (L1: hi, lo per k-block and head pair) + 16 + 4
+constexpr size_t kSmemBytes2 = 1024 + (size_t)kNA * kStageA + (size_t)kNACT * kStageA + (size_t)kNW * kPanelBytes + 512;
+
+struct Bars2 {
+    uint64_t a_full[kNA], a_empty[kNA];
+    uint64_t w_full[kNW], w_empty[kNW], w_peer[kNW];
+    uint64_t act_full[kNACT], act_empty[kNACT];
+    uint64_t tm_full[4], tm_empty[4];
+    uint32_t tmem_base;
+};
+
+// ---- cluster / cta_group::2 PTX ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory object in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
+    }
+}
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %4, 0;\nmov.b64 da, {%1, %5};\nmov.b64 db, {%2, %5};\n"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n}"
+                 ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi) : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs once all previously issued MMAs have completed
+__device__ __forceinline__ void umma2_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait_cluster_t(uint64_t *bar, uint32_t parity, unsigned long long *acc) {
+    if (acc == nullptr) { mbar_wait_cluster(bar, parity); return; }
+    const long long t0 = clock64();
+    mbar_wait_cluster(bar, parity);
+    *acc += (unsigned long long)(clock64() - t0);
+}
+
+// One arrival on a barrier the leader's issuer waits on: local in the leader, remote from the peer.
+struct LeaderBar {
+    uint32_t rank;
+    __device__ __forceinline__ void arrive(uint64_t *bar) const {
+        if (rank == 0) mbar_arrive(bar);
+        else mbar_arrive_remote(mapa(smem_u32(bar), 0));
+    }
+};
+
+__global__ void __launch_bounds__(kThreads, 1) query_tc2_kernel(const TcParams q) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *ringA = smem;                                      // [kNA][hi 16K | lo 16K]
+    uint8_t *ringAct = ringA + (size_t)kNA * kStageA;           // [kNACT][hi 16K | lo 16K]
+    uint8_t *ringW = ringAct + (size_t)kNACT * kStageA;         // [kNW][16K]
+    Bars2 *bars = reinterpret_cast<Bars2 *>(ringW + (size_t)kNW * kPanelBytes);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const LeaderBar lb{rank};
+    // tracing (CHORE_B200_TC_TRACE): wait cycles of the issuer, one row per cluster
+    unsigned long long dbg_local[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const bool dbg_on = q.dbg != nullptr && lane == 0 && rank == 0 && (warp == 1 || warp == 2 || warp == 6);
+    const long long dbg_t0 = clock64();
+#define DBG(i) (dbg_on ? &dbg_local[i] : nullptr)
+
+    if (threadIdx.x == 0) {
+        // barriers the issuer waits on collect the arrivals of both CTAs (only the leader's copies are used)
+        for (int i = 0; i < kNA; ++i) { mbar_init(&bars->a_full[i], 8); mbar_init(&bars->a_empty[i], 1); }
+        for (int i = 0; i < kNACT; ++i) { mbar_init(&bars->act_full[i], 8); mbar_init(&bars->act_empty[i], 1); }
+        for (int i = 0; i < kNW; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); mbar_init(&bars->w_peer[i], 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&bars->tm_full[i], 1); mbar_init(&bars->tm_empty[i], 8); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {   // TMEM: all 512 columns in both CTAs (4 heads x 128 fp32 accumulator columns)
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&bars->tmem_base)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();          // barrier inits of the partner are visible before any remote arrive / multicast commit
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, bars->tmem_base, 0);
+
+    const long long n_clusters = gridDim.x >> 1, cid = blockIdx.x >> 1;
+    const long long total_pairs = (q.total_tiles + 1) >> 1;
+    // this CTA's tile of pair j is 2j + rank; the last pair of an odd tile count has a dead second tile (no live rows)
+
+    if (warp == 0) {
+        // =============================== weight producer (this CTA's half of every panel) ===============================
+        uint32_t u = 0;
+        for (long long pair = cid; pair < total_pairs; pair += n_clusters) {
+            for (int i = 0; i < kSlotsPerPair; ++i, ++u) {
+                const int s = u % kNW;
+                mbar_wait(&bars->w_empty[s], ((u / kNW) & 1) ^ 1);
+                if (elect_one()) {
+                    uint8_t *dst = ringW + (size_t)s * kPanelBytes;
+                    if (i < kL1Blocks * 4) {
+                        // layer 1, slot order (kb, pair p, hi|lo): the full 16 KB panel of head 2p + rank
+                        const int kb = i >> 2, p = (i >> 1) & 1, hl = i & 1;
+                        const size_t unit = (size_t)(kb * 4 + 2 * p + (int)rank) * 2 + hl;
+                        mbar_arrive_expect_tx(&bars->w_full[s], kPanelBytes);
+                        bulk_g2s(dst, q.wstream + unit * kPanelBytes, kPanelBytes, &bars->w_full[s]);
+                    } else if (i < kL1Blocks * 4 + 16) {
+                        // layers 2, 3, slot order (layer, head, kb): output rows 64 rank .. +63 of the hi and of the lo panel
+                        const int j = i - kL1Blocks * 4;
+                        const size_t unit = (size_t)kL1Blocks * 8 + (size_t)j * 2;
+                        mbar_arrive_expect_tx(&bars->w_full[s], kPanelBytes);
+                        bulk_g2s(dst, q.wstream + unit * kPanelBytes + (size_t)rank * 8192, 8192, &bars->w_full[s]);
+                        bulk_g2s(dst + 8192, q.wstream + (unit + 1) * kPanelBytes + (size_t)rank * 8192, 8192, &bars->w_full[s]);
+                    } else {
+                        // last layer: 8 of the 16 (padded) output rows of [kb0 hi | kb0 lo | kb1 hi | kb1 lo]
+                        const int hd = i - (kL1Blocks * 4 + 16);
+                        const uint8_t *src = q.wstream + (size_t)kBigUnits * kPanelBytes + (size_t)hd * kSmallPanelBytes;
+                        mbar_arrive_expect_tx(&bars->w_full[s], 4096);
+#pragma unroll
+                        for (int b4 = 0; b4 < 4; ++b4) bulk_g2s(dst + b4 * 1024, src + b4 * 2048 + (size_t)rank * 1024, 1024, &bars->w_full[s]);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1 && rank == 1) {
+        // =============================== peer: relay "my half has landed" to the leader ===============================
+        uint32_t u = 0;
+        for (long long pair = cid; pair < total_pairs; pair += n_clusters)
+            for (int i = 0; i < kSlotsPerPair; ++i, ++u) {
+                const int s = u % kNW;
+                mbar_wait(&bars->w_full[s], (u / kNW) & 1);
+                if (lane == 0) mbar_arrive_remote(mapa(smem_u32(&bars->w_peer[s]), 0));
+                __syncwarp();
+            }
+    } else if (warp == 1) {
+        // =============================== MMA issuer (leader) ===============================
+        constexpr uint32_t idesc256 = make_idesc(256, 256), idesc128 = make_idesc(256, 128), idesc16 = make_idesc(256, 16);
+        const uint32_t ringA_lo = desc_lo(smem_u32(ringA)), ringAct_lo = desc_lo(smem_u32(ringAct)), ringW_lo = desc_lo(smem_u32(ringW));
+        constexpr uint32_t kStageLo = kStageA >> 4, kPanelLo = kPanelBytes >> 4;
+        uint32_t u = 0, ablk = 0, actblk = 0, tile_i = 0;
+        auto wait_w = [&](uint32_t uu) {      // both halves of ring slot uu % kNW have landed
+            const int s = uu % kNW;
+            mbar_wait_t(&bars->w_full[s], (uu / kNW) & 1, DBG(2));
+            mbar_wait_cluster_t(&bars->w_peer[s], (uu / kNW) & 1, DBG(3));
+            tc_fence_after();
+            return ringW_lo + s * kPanelLo;
+        };
+        for (long long pair = cid; pair < total_pairs; pair += n_clusters, ++tile_i) {
+            // ---- layer 1: 6 k-blocks x 2 head pairs, N = 256 (head 2p in the leader's panel, 2p + 1 in the peer's) ----
+            for (int kb = 0; kb < kL1Blocks; ++kb, ++ablk) {
+                const int sa = ablk % kNA;
+                mbar_wait_cluster_t(&bars->a_full[sa], (ablk / kNA) & 1, DBG(0));
+                tc_fence_after();
+                const uint32_t a_hi = ringA_lo + sa * kStageLo, a_lo = a_hi + kPanelLo;
+                const bool last = kb == kL1Blocks - 1;       // the xyz block holds 16 channels: one k-step
+#pragma unroll 1
+                for (int p = 0; p < 2; ++p) {
+                    if (kb == 0) {   // both accumulators of the pair must have been drained (previous tile pair)
+                        mbar_wait_cluster_t(&bars->tm_empty[2 * p], (tile_i & 1) ^ 1, DBG(1));
+                        mbar_wait_cluster_t(&bars->tm_empty[2 * p + 1], (tile_i & 1) ^ 1, DBG(1));
+                        tc_fence_after();
+                    }
+                    const uint32_t d = tmem_base + p * 256;
+                    const uint32_t w0 = wait_w(u);                       // hi panels: a_hi*w_hi + a_lo*w_hi
+                    if (elect_one()) {
+                        umma2_f16(d, a_hi, w0, idesc256, kb != 0);
+                        umma2_f16(d, a_lo, w0, idesc256, 1);
+                        if (!last) {
+#pragma unroll
+                            for (int ks = 1; ks < 4; ++ks) {
+                                umma2_f16(d, a_hi + 2 * ks, w0 + 2 * ks, idesc256, 1);
+                                umma2_f16(d, a_lo + 2 * ks, w0 + 2 * ks, idesc256, 1);
+                            }
+                        }
+                        umma2_commit(&bars->w_empty[u % kNW]);
+                    }
+                    __syncwarp();
+                    const uint32_t w1 = wait_w(u + 1);                   // lo panels: a_hi*w_lo
+                    if (elect_one()) {
+                        umma2_f16(d, a_hi, w1, idesc256, 1);
+                        if (!last) {
+#pragma unroll
+                            for (int ks = 1; ks < 4; ++ks) umma2_f16(d, a_hi + 2 * ks, w1 + 2 * ks, idesc256, 1);
+                        }
+                        umma2_commit(&bars->w_empty[(u + 1) % kNW]);
+                        if (last) { umma2_commit(&bars->tm_full[2 * p]); umma2_commit(&bars->tm_full[2 * p + 1]); }
+                        if (p == 1) umma2_commit(&bars->a_empty[sa]);
+                    }
+                    __syncwarp();
+                    u += 2;
+                }
+            }
+            // ---- layers 2, 3 (N = 128) and 4 (N = 16): per head, A operand = the two CTAs' activation blocks ----
+#pragma unroll 1
+            for (int layer = 1; layer < 4; ++layer) {
+#pragma unroll 1
+                for (int h = 0; h < 4; ++h) {
+                    const uint32_t d = tmem_base + h * 128;
+                    // both activation blocks must be complete before the accumulator is overwritten
+                    const int st0 = actblk % kNACT, st1 = (actblk + 1) % kNACT;
+                    mbar_wait_cluster_t(&bars->act_full[st0], (actblk / kNACT) & 1, DBG(4));
+                    mbar_wait_cluster_t(&bars->act_full[st1], ((actblk + 1) / kNACT) & 1, DBG(4));
+                    actblk += 2;
+                    tc_fence_after();
+                    if (layer < 3) {
+#pragma unroll 1
+                        for (int kb = 0; kb < 2; ++kb) {
+                            const int sa = kb == 0 ? st0 : st1;
+                            const uint32_t a_hi = ringAct_lo + sa * kStageLo, a_lo = a_hi + kPanelLo;
+                            const uint32_t w_hi = wait_w(u), w_lo = w_hi + (8192 >> 4);     // [hi rows | lo rows] in one slot
+                            if (elect_one()) {
+                                // same accumulation order as query_tc_kernel (bit-identical results): all w_hi terms, then w_lo
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) {
+                                    umma2_f16(d, a_hi + 2 * ks, w_hi + 2 * ks, idesc128, (kb | ks) != 0);
+                                    umma2_f16(d, a_lo + 2 * ks, w_hi + 2 * ks, idesc128, 1);
+                                }
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) umma2_f16(d, a_hi + 2 * ks, w_lo + 2 * ks, idesc128, 1);
+                                umma2_commit(&bars->w_empty[u % kNW]);
+                                umma2_commit(&bars->act_empty[sa]);
+                                if (kb == 1) umma2_commit(&bars->tm_full[h]);
+                            }
+                            __syncwarp();
+                            u += 1;
+                        }
+                    } else {
+                        const uint32_t w = wait_w(u);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int kb = 0; kb < 2; ++kb) {
+                                const uint32_t a_hi = ringAct_lo + (kb == 0 ? st0 : st1) * kStageLo, a_lo = a_hi + kPanelLo;
+                                const uint32_t w_hi = w + kb * (2048 >> 4), w_lo = w_hi + (1024 >> 4);
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) {
+                                    umma2_f16(d, a_hi + 2 * ks, w_hi + 2 * ks, idesc16, (kb | ks) != 0);
+                                    umma2_f16(d, a_lo + 2 * ks, w_hi + 2 * ks, idesc16, 1);
+                                    umma2_f16(d, a_hi + 2 * ks, w_lo + 2 * ks, idesc16, 1);
+                                }
+                                umma2_commit(&bars->act_empty[kb == 0 ? st0 : st1]);
+                            }
+                            umma2_commit(&bars->w_empty[u % kNW]);
+                            umma2_commit(&bars->tm_full[h]);
+                        }
+                        __syncwarp();
+                        u += 1;
+                    }
+                }
+            }
+        }
+    } else if (warp < kEpiWarp0) {
+        // =============================== gather warps ===============================
+        const int g = warp - kGatherWarp0;
+        const int half = lane >> 4, l16 = lane & 15;
+        uint32_t ablk = 0;
+        for (long long pair = cid; pair < total_pairs; pair += n_clusters) {
+            const long long tile = 2 * pair + rank;
+            const bool dead = tile >= q.total_tiles;
+            const int b = q.grid_mode ? q.batch_index : (dead ? 0 : (int)(tile / q.tiles_per_b));
+            const long long n0 = dead ? q.n_count : (tile % q.tiles_per_b) * kTileM;
+            const float ccx = __ldg(q.crop_center + b * 2), ccy = __ldg(q.crop_center + b * 2 + 1);
+            const float *F = q.feat + (size_t)b * q.fh * q.fw * kFeatC;
+            const float *S = q.skip + (size_t)b * (2 * q.fh) * (2 * q.fw) * kSkipC;
+            float my_x = 0.f, my_y = 0.f, my_z = 1.f, my_nx, my_ny;
+            if (n0 + g * 32 + lane < q.n_count) load_point(q, b, n0 + g * 32 + lane, my_x, my_y, my_z);
+            project_tc(my_x, my_y, my_z, ccx, ccy, my_nx, my_ny);
+            if (dead) { my_nx = 4.f; my_ny = 4.f; }                 // outside the image: no loads
+            for (int kb = 0; kb < kL1Blocks; ++kb, ++ablk) {
+                const int sa = ablk % kNA;
+                mbar_wait_t(&bars->a_empty[sa], ((ablk / kNA) & 1) ^ 1, DBG(0));
+                uint8_t *hi = ringA + (size_t)sa * kStageA, *lo = hi + kPanelBytes;
+                if (kb < 5) {
+                    const bool is_feat = kb < 4;
+                    gather_kblock((is_feat ? F + kb * 64 : S) + l16 * 4, is_feat ? q.fh : 2 * q.fh, is_feat ? q.fw : 2 * q.fw,
+                                  is_feat ? kFeatC : kSkipC, my_nx, my_ny, g, half, l16, hi, lo);
+                } else {
+                    // z_feat = [x, y, z - 2.2] (model/chore.py:128-129) + 13 zero channels: one k-step, lane = row
+                    const int r = g * 32 + lane;
+                    uint32_t h01, l01, h23, l23;
+                    split2(my_x, my_y, h01, l01);
+                    split2(__fsub_rn(my_z, 2.2f), 0.f, h23, l23);
+                    *reinterpret_cast<uint4 *>(hi + sw128(r, 0)) = make_uint4(h01, h23, 0u, 0u);
+                    *reinterpret_cast<uint4 *>(lo + sw128(r, 0)) = make_uint4(l01, l23, 0u, 0u);
+                    *reinterpret_cast<uint4 *>(hi + sw128(r, 1)) = make_uint4(0u, 0u, 0u, 0u);
+                    *reinterpret_cast<uint4 *>(lo + sw128(r, 1)) = make_uint4(0u, 0u, 0u, 0u);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) lb.arrive(&bars->a_full[sa]);
+            }
+        }
+    } else {
+        // =============================== epilogue warps ===============================
+        const int e = warp - kEpiWarp0;              // 0..7
+        const int quarter = warp & 3;                // TMEM lane quarter this warp may access
+        const int colhalf = e >> 2;                  // 0: columns 0-63, 1: columns 64-127
+        const int row = quarter * 32 + lane;         // point of the tile owned by this thread
+        uint32_t actblk = 0;
+        for (long long pair = cid; pair < total_pairs; pair += n_clusters) {
+            const long long tile = 2 * pair + rank;
+            const bool dead = tile >= q.total_tiles;
+            const int b = q.grid_mode ? q.batch_index : (dead ? 0 : (int)(tile / q.tiles_per_b));
+            const long long n = dead ? q.n_count : (tile % q.tiles_per_b) * kTileM + row;
+            const bool live = n < q.n_count;
+            bool inimg = false;
+            {
+                float x = 0.f, y = 0.f, z = 1.f, nx, ny;
+                if (live) load_point(q, b, n, x, y, z);
+                project_tc(x, y, z, __ldg(q.crop_center + b * 2), __ldg(q.crop_center + b * 2 + 1), nx, ny);
+                inimg = (nx >= -1.0f) && (nx <= 1.0f) && (ny >= -1.0f) && (ny <= 1.0f);
+                if (q.in_img && live && e < 4) q.in_img[(size_t)b * q.N + q.n_start + n] = inimg;
+            }
+#pragma unroll 1
+            for (int layer = 0; layer < 4; ++layer) {
+#pragma unroll 1
+                for (int h = 0; h < 4; ++h) {
+                    if (layer == 3 && (h & 1) != colhalf) continue;      // last layer: the heads are split between the groups
+                    if (layer < 3) {
+                        // bias + ReLU + hi/lo split -> activation k-block `colhalf` of head h
+                        mbar_wait_t(&bars->tm_full[h], layer & 1, DBG(0));         // 4 completions per tile: parity = layer & 1
+                        tc_fence_after();
+                        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + h * 128 + colhalf * 64;
+                        const float *bias = (layer == 0 ? q.b1 : (layer == 1 ? q.b2 : q.b3)) + h * 128 + colhalf * 64;
+                        const uint32_t blk = actblk + colhalf;
+                        const int sa = blk % kNACT;
+                        mbar_wait_t(&bars->act_empty[sa], ((blk / kNACT) & 1) ^ 1, DBG(1));
+                        uint8_t *hi = ringAct + (size_t)sa * kStageA, *lo = hi + kPanelBytes;
+#pragma unroll
+                        for (int part = 0; part < 2; ++part) {
+                            uint32_t v[32];
+                            tmem_ld32(taddr + part * 32, v);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int c8 = 0; c8 < 4; ++c8) {     // 8 columns = one 16-byte chunk of fp16
+                                uint32_t hh[4], ll[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const int c = c8 * 8 + j * 2;
+                                    const float2 bb = __ldg(reinterpret_cast<const float2 *>(bias + part * 32 + c));
+                                    const float a0 = fmaxf(__uint_as_float(v[c]) + bb.x, 0.f);
+                                    const float a1 = fmaxf(__uint_as_float(v[c + 1]) + bb.y, 0.f);
+                                    split2_pos(a0, a1, hh[j], ll[j]);
+                                }
+                                const uint32_t off = sw128(row, part * 4 + c8);
+                                *reinterpret_cast<uint4 *>(hi + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+                                *reinterpret_cast<uint4 *>(lo + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+                            }
+                        }
+                        tc_fence_before();
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) lb.arrive(&bars->act_full[sa]);
+                        actblk += 2;
+                    } else {
+                        const int nout = head_out_tc(h);
+                        mbar_wait_t(&bars->tm_full[h], layer & 1, DBG(2));
+                        tc_fence_after();
+                        uint32_t v[16];
+                        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + h * 128, v);
+                        tmem_ld_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) lb.arrive(&bars->tm_empty[h]);    // the next pair's layer 1 may overwrite head h
+                        if (live) {
+                            float *outp = q.out[h] + ((size_t)b * nout) * q.N + q.n_start + n;
+#pragma unroll
+                            for (int o = 0; o < 14; ++o) {
+                                if (o < nout) {
+                                    float val = __uint_as_float(v[o]) + __ldg(q.b4 + h * 16 + o);
+                                    if (h == 0 && !inimg) val = 5.0f;          // model/chore.py:147-150
+                                    outp[(size_t)o * q.N] = val;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    if (dbg_on) {
+        dbg_local[7] = (unsigned long long)(clock64() - dbg_t0);
+        const int rowsel = warp == 1 ? 0 : (warp == 2 ? 1 : 2);
+        for (int i = 0; i < 8; ++i) q.dbg[((size_t)(blockIdx.x >> 1) * 3 + rowsel) * 8 + i] = dbg_local[i];
+    }
+#undef DBG
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();          // no CTA may exit (or free TMEM) while its partner can still signal it
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+}   // namespace
+
+// Experimental (round 1): bit-identical to query_tc_kernel and passes the whole parity suite, but 3-6 % slower at the
+// moment, so it is opt-in: CHORE_B200_QUERY_2CTA=1.
+bool query_tc2_enabled() {
+    const char *e = getenv("CHORE_B200_QUERY_2CTA");      // read per call: the parity test toggles it
+    return e != nullptr && e[0] == '1';
+}
+
+// Forward for head_mask == all heads on CTA pairs; same arguments as query_tc_launch.
+int query_tc2_launch(chore_handle *h, const float *feat, const float *skip, int fh, int fw, const float *points,
+                     const float *crop_center, int B, long long N, long long n_start, long long n_count, int grid_mode,
+                     int batch_index, const int *res, const double *step, const double *bmin, float *const outs[4],
+                     unsigned char *in_img, cudaStream_t st) {
+    TcParams q{};
+    q.feat = feat; q.skip = skip; q.fh = fh; q.fw = fw;
+    q.points = points; q.crop_center = crop_center;
+    q.B = B; q.N = N; q.n_start = n_start; q.n_count = n_count;
+    q.grid_mode = grid_mode; q.batch_index = batch_index;
+    if (grid_mode) {
+        q.ry = res[1]; q.rz = res[2];
+        for (int i = 0; i < 3; ++i) { q.step[i] = step[i]; q.bmin[i] = bmin[i]; }
+    }
+    q.head_mask = 15u;
+    for (int i = 0; i < 4; ++i) q.out[i] = outs[i];
+    q.in_img = in_img;
+    const MlpWeights &m = h->mlp;
+    q.wstream = m.wstream; q.b1 = m.b1; q.b2 = m.b2; q.b3 = m.b3; q.w4 = m.w4; q.b4 = m.b4;
+    q.tiles_per_b = (n_count + kTileM - 1) / kTileM;
+    q.total_tiles = q.tiles_per_b * (grid_mode ? 1 : B);
+    static bool configured = false;
+    if (!configured) {
+        CHORE_CUDA(cudaFuncSetAttribute(query_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes2));
+        configured = true;
+    }
+    const long long pairs = (q.total_tiles + 1) / 2;
+    const long long clusters = pairs < h->sm_count / 2 ? pairs : h->sm_count / 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(2 * clusters));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes2;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    static const bool trace = getenv("CHORE_B200_TC_TRACE") != nullptr;
+    unsigned long long *dbg = nullptr;
+    if (trace) {
+        CHORE_CUDA(cudaMalloc(&dbg, (size_t)clusters * 24 * sizeof(unsigned long long)));
+        CHORE_CUDA(cudaMemsetAsync(dbg, 0, (size_t)clusters * 24 * sizeof(unsigned long long), st));
+        q.dbg = dbg;
+    }
+    CHORE_CUDA(cudaLaunchKernelEx(&cfg, query_tc2_kernel, q));
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    if (trace) {   // debugging aid: synchronous, prints the issuer's mean wait cycles per tile pair
+        unsigned long long *hb = (unsigned long long *)malloc((size_t)clusters * 24 * sizeof(unsigned long long));
+        CHORE_CUDA(cudaMemcpyAsync(hb, dbg, (size_t)clusters * 24 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CHORE_CUDA(cudaStreamSynchronize(st));
+        CHORE_CUDA(cudaFree(dbg));
+        static const char *names[3][8] = {{"mma:a_full", "mma:tm_empty", "mma:w_full(local)", "mma:w_peer", "mma:act_full", "", "", "total"},
+                                          {"gather:a_empty", "", "", "", "", "", "", ""},
+                                          {"epi:tm_full(L1-3)", "epi:act_empty", "epi:tm_full(L4)", "", "", "", "", ""}};
+        double sum[24] = {0};
+        for (long long c = 0; c < clusters; ++c)
+            for (int i = 0; i < 24; ++i) sum[i] += (double)hb[c * 24 + i];
+        free(hb);
+        const double per = (double)pairs / (double)clusters;
+        fprintf(stderr, "[tc2-trace] pairs/cluster %.1f; leader-CTA cycles per tile pair:", per);
+        for (int r = 0; r < 3; ++r)
+            for (int i = 0; i < 8; ++i)
+                if (names[r][i][0] && (r == 0 || i < 3)) fprintf(stderr, " %s=%.0f", names[r][i], sum[r * 8 + i] / (double)clusters / per);
+        fprintf(stderr, "\n");
+    }
+    return CHORE_OK;
+}

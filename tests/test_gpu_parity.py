@@ -650,3 +650,34 @@ def test_query_bwd_concurrent_heads_equal_sequential(net):
         seq, con = run(base, gs), run(base * k, gs)
         assert torch.isfinite(seq).all() and seq.abs().max() > 0
         assert torch.equal(seq, con), (k, (seq - con).abs().max().item())
+
+
+def test_cta_pair_kernel_is_bit_identical(net, monkeypatch):
+    """query_tc2_kernel (tcgen05 cta_group::2: two CTAs of a cluster share every weight panel, layer 1 as N = 256 MMAs; opt-in
+    with CHORE_B200_QUERY_2CTA=1) must reproduce query_tc_kernel bit for bit: same operands, same accumulation order.  Covers an
+    odd tile count (dead second tile of the last pair), B > 1, out-of-image points and the dense-grid entry point."""
+    feat, tmpx = O.synth_features(101, B=2)
+    set_maps(net, feat, tmpx)
+    f, s = net._maps()
+    cc = torch.tensor([[1008., 995.], [990., 1001.]], device=DEV)
+    for N in (1, 129, 1000, 20000):
+        pts = torch.cat([O.synth_points("frustum", 102 + N, 2, N - N // 3), O.synth_points("init_box", 103, 2, N // 3)], 1).to(DEV)
+        monkeypatch.setenv("CHORE_B200_QUERY_2CTA", "0")
+        ref, m0 = net.handle.query_fwd(f, s, pts, cc, 15, want_in_img=True)
+        monkeypatch.setenv("CHORE_B200_QUERY_2CTA", "1")
+        got, m1 = net.handle.query_fwd(f, s, pts, cc, 15, want_in_img=True)
+        torch.cuda.synchronize()
+        assert torch.equal(m0, m1)
+        for h in range(4):
+            assert torch.equal(got[h], ref[h]), (N, h, (got[h] - ref[h]).abs().max().item())
+    res, pmin, pmax = (24, 20, 28), (-3.0, -0.9, 0.2), (3.0, 1.8, 4.0)
+    total = res[0] * res[1] * res[2]
+    outs = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("CHORE_B200_QUERY_2CTA", flag)
+        o = [torch.zeros(c, total, device=DEV) for c in (2, 9, 14, 6)]
+        net.handle.query_grid(f, s, cc, 1, res, pmin, pmax, 100, total - 100, 15, o)
+        torch.cuda.synchronize()
+        outs[flag] = o
+    for a, b in zip(outs["0"], outs["1"]):
+        assert torch.equal(a, b)
