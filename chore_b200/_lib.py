@@ -62,6 +62,8 @@ SIGNATURES = {
     "chore_fit_pose_prior_grads": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _P, _P, _P, _P]),
     "chore_fit_obj_field_grads": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P]),
     "chore_add_rowvec": (_I, [_P, _P, _P, _I, _I, _F, _P]),
+    "chore_surface_clamp_grad": (_I, [_P, _P, _I, _F, _I, _I, _P, _P]),
+    "chore_surface_step": (_I, [_P, _P, _P, _P, _I, _F, _I, _I, _P, _P]),
     "chore_adam_step": (_I, [_P, C.POINTER(AdamEntry), _I, _F, _F, _F, _F, _P, _P]),
     "chore_rigid_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P]),
     "chore_rigid_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
@@ -333,6 +335,22 @@ class Handle:
         check_cuda(x, v)
         with torch.cuda.device(self.device):
             self._check(self.lib.chore_add_rowvec(self.h, x.data_ptr(), v.data_ptr(), x.shape[0], x.shape[1], alpha, _stream()))
+
+    def surface_clamp_grad(self, df, df_idx: int, threshold: float):
+        check_cuda(df)
+        g_df = torch.empty_like(df)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.chore_surface_clamp_grad(self.h, df.data_ptr(), df_idx, threshold, df.shape[0], df.shape[2], g_df.data_ptr(),
+                                                          _stream()))
+        return g_df
+
+    def surface_step(self, points, g_points, df, df_idx: int, threshold: float):
+        check_cuda(points, g_points, df)
+        out = torch.empty_like(points)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.chore_surface_step(self.h, points.data_ptr(), g_points.data_ptr(), df.data_ptr(), df_idx, threshold,
+                                                    points.shape[0], points.shape[1], out.data_ptr(), _stream()))
+        return out
 
     def adam_step(self, entries, n: int, lr: float, beta1: float, beta2: float, eps: float, step) -> None:
         with torch.cuda.device(self.device):

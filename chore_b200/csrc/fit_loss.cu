@@ -231,6 +231,30 @@ __global__ void __launch_bounds__(256) add_rowvec_kernel(float *__restrict__ x, 
     x[i] += alpha * v[b * 3 + c];
 }
 
+// ---- surface projection step (Generator.approx_surface, recon/generator.py:50-79) --------------------------------
+// t = clamp(df[:, k], max=thr); t.sum().backward()  =>  g_df[:, k] = (df[:, k] <= thr), the other channel 0
+__global__ void __launch_bounds__(256) surface_clamp_grad_kernel(const float *__restrict__ df, int k, float thr, int B, int N,
+                                                                  float *__restrict__ g_df) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * N) return;
+    const int b = (int)(i / N), n = (int)(i - (long long)b * N);
+    g_df[((size_t)b * 2 + k) * N + n] = df[((size_t)b * 2 + k) * N + n] <= thr ? 1.f : 0.f;
+    g_df[((size_t)b * 2 + (1 - k)) * N + n] = 0.f;
+}
+// p <- p - normalize(g, eps = 1e-12) * min(df[:, k], thr)     (F.normalize: g / max(||g||_2, eps))
+__global__ void __launch_bounds__(256) surface_step_kernel(const float *__restrict__ pts, const float *__restrict__ g, const float *__restrict__ df,
+                                                            int k, float thr, int B, int N, float *__restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * N) return;
+    const int b = (int)(i / N), n = (int)(i - (long long)b * N);
+    const float gx = g[i * 3], gy = g[i * 3 + 1], gz = g[i * 3 + 2];
+    const float nrm = fmaxf(sqrtf(gx * gx + gy * gy + gz * gz), 1e-12f);
+    const float t = fminf(df[((size_t)b * 2 + k) * N + n], thr);
+    out[i * 3] = pts[i * 3] - gx / nrm * t;
+    out[i * 3 + 1] = pts[i * 3 + 1] - gy / nrm * t;
+    out[i * 3 + 2] = pts[i * 3 + 2] - gz / nrm * t;
+}
+
 // ---- Adam ------------------------------------------------------------------------------------------------------
 struct AdamArgs {
     chore_adam_entry e[CHORE_ADAM_MAX_ENTRIES];
@@ -332,5 +356,21 @@ extern "C" int chore_adam_step(chore_handle *h, const chore_adam_entry *entries,
         a.e[i] = entries[i];
     }
     CHORE_LAUNCH(adam_step_kernel, 1, 256, 0, static_cast<cudaStream_t>(stream), a, lr, beta1, beta2, eps, step);
+    return CHORE_OK;
+}
+
+extern "C" int chore_surface_clamp_grad(chore_handle *h, const float *df, int df_idx, float threshold, int B, int N, float *g_df,
+                                        void *stream) {
+    CHORE_CHECK(h && df && g_df && B > 0 && N > 0 && (df_idx == 0 || df_idx == 1), "bad arguments");
+    CHORE_LAUNCH(surface_clamp_grad_kernel, (unsigned)(((long long)B * N + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream), df, df_idx,
+                 threshold, B, N, g_df);
+    return CHORE_OK;
+}
+
+extern "C" int chore_surface_step(chore_handle *h, const float *points, const float *g_points, const float *df, int df_idx, float threshold,
+                                  int B, int N, float *out_points, void *stream) {
+    CHORE_CHECK(h && points && g_points && df && out_points && B > 0 && N > 0 && (df_idx == 0 || df_idx == 1), "bad arguments");
+    CHORE_LAUNCH(surface_step_kernel, (unsigned)(((long long)B * N + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream), points, g_points, df,
+                 df_idx, threshold, B, N, out_points);
     return CHORE_OK;
 }

@@ -15,7 +15,10 @@ from .net import heads
 
 class Generator:
     def __init__(self, model, threshold: float = 2.0, filter_val: float = 0.004, sparse_thres: float = 0.03,
-                 device="cuda:0"):
+                 device="cuda:0", fused: bool = True):
+        """fused: run approx_surface through the autograd-free kernel sequence when the model is a chore_b200.CHORE
+        (same values up to the last bit of F.normalize's norm); False keeps the reference's autograd formulation."""
+        self.fused = fused
         self.model = model
         self.threshold = threshold
         self.filter_val = filter_val
@@ -28,6 +31,8 @@ class Generator:
     def approx_surface(self, model, samples, num_steps, query_input, df_type):
         """num_steps x { query; t = clamp(df_k, max=thr); t.sum().backward(); p <- p - normalize(grad) * t }"""
         df_idx = 0 if df_type == "human" else 1
+        if self.fused and hasattr(model, "handle") and samples.is_cuda and num_steps > 0:
+            return self._approx_surface_fused(model, samples, num_steps, query_input, df_idx)
         preds = None
         for step in range(num_steps):
             # only the distance head drives the projection; the other three are needed from the LAST query only
@@ -42,6 +47,31 @@ class Generator:
             samples = samples.detach()
             samples.requires_grad = True
         return samples, preds
+
+    @torch.no_grad()
+    def _approx_surface_fused(self, model, samples, num_steps, query_input, df_idx):
+        """The same projection loop without autograd: per step  query (df head only; all heads on the last step, whose
+        preds are returned) -> d clamp(df).sum() / d df -> query adjoint -> p - normalize(grad) * t , i.e. two query
+        launches and two elementwise kernels instead of an autograd round trip and ~10 eager ops."""
+        h = model.handle
+        feat, skip = model._maps()
+        cc = query_input["crop_center"].detach().to(samples.device, torch.float32).contiguous()
+        p = samples.detach().float().contiguous()
+        B, N = p.shape[0], p.shape[1]
+        outs = None
+        for step in range(num_steps):
+            last = step == num_steps - 1
+            mask = getattr(model, "head_mask", _lib.HEAD_ALL) | _lib.HEAD_DF if last else _lib.HEAD_DF
+            outs, _ = h.query_fwd(feat, skip, p, cc, mask)
+            g_df = h.surface_clamp_grad(outs[0], df_idx, float(self.threshold))
+            g_p = h.query_bwd(feat, skip, p, cc, [g_df, None, None, None])
+            p = h.surface_step(p, g_p, outs[0], df_idx, float(self.threshold))
+        z = lambda c: p.new_zeros(B, c, 0)
+        df, pca, parts, centers = [o if o is not None else z(c) for o, c in zip(outs, _lib.HEAD_OUT)]
+        preds = (df, pca.view(B, 3, 3, -1), parts, centers)
+        model.preds = preds
+        p.requires_grad = True
+        return p, preds
 
     def init_samples(self, sample_num, batch_size=1):
         """recon/generator.py:275-282 (only batch element 0 is rescaled there; kept)."""

@@ -211,6 +211,16 @@ int chore_fit_obj_field_grads(chore_handle *h, const float *obj, const float *df
 /* x (B,N,3) += alpha * v (B,3) broadcast over N */
 int chore_add_rowvec(chore_handle *h, float *x, const float *v, int B, int N, float alpha, void *stream);
 
+/* ---- surface projection step of Generator.approx_surface (recon/generator.py:50-79): the two elementwise
+ *      stages around the field query and its gradient.  df (B,2,N), df_idx 0 = human / 1 = object. ------ */
+/* gradient of clamp(df[:, df_idx], max=threshold).sum() w.r.t. df: g_df (B,2,N) */
+int chore_surface_clamp_grad(chore_handle *h, const float *df, int df_idx, float threshold, int B, int N,
+                             float *g_df, void *stream);
+/* out = points - F.normalize(g_points, dim=-1, eps=1e-12) * min(df[:, df_idx], threshold): points, g_points, out (B,N,3);
+ * out may alias points */
+int chore_surface_step(chore_handle *h, const float *points, const float *g_points, const float *df, int df_idx,
+                       float threshold, int B, int N, float *out_points, void *stream);
+
 /* torch.optim.Adam.step (weight_decay 0, amsgrad off) for up to CHORE_ADAM_MAX_ENTRIES small tensors in one
  * launch.  `step` is a device int32 step counter (read, then incremented by the kernel: graph-replay safe). */
 #define CHORE_ADAM_MAX_ENTRIES 8

@@ -681,3 +681,28 @@ def test_cta_pair_kernel_is_bit_identical(net, monkeypatch):
         outs[flag] = o
     for a, b in zip(outs["0"], outs["1"]):
         assert torch.equal(a, b)
+
+
+def test_fused_surface_projection_matches_autograd_path(net):
+    """Generator.approx_surface (recon/generator.py:50-79): the autograd-free kernel sequence (query -> clamp gradient ->
+    query adjoint -> normalised step) against the reference's autograd formulation on the same kernels.  One step is compared
+    tightly (identical inputs); F.normalize's norm may differ in the last bit, so a few steps are compared with a loose bound
+    on all but a vanishing fraction of the points (the projection is discontinuous across texel / ReLU boundaries)."""
+    import chore_b200
+    feat, tmpx = O.synth_features(111, B=2)
+    set_maps(net, feat, tmpx)
+    cc = torch.tensor([[1008., 995.], [1000., 990.]], device=DEV)
+    q = {"crop_center": cc}
+    pts = O.synth_points("frustum", 112, 2, 3000).to(DEV)
+    fused, plain = chore_b200.Generator(net, device=DEV, fused=True), chore_b200.Generator(net, device=DEV, fused=False)
+    for df_type in ("human", "object"):
+        a, pa = fused.approx_surface(net, pts.clone().requires_grad_(True), 1, q, df_type)
+        b, pb = plain.approx_surface(net, pts.clone().requires_grad_(True), 1, q, df_type)
+        assert a.requires_grad and a.shape == b.shape
+        assert rel_err(a, b) < 1e-5, rel_err(a, b)
+        for x, y in zip(pa, pb):
+            assert torch.equal(x, y)                       # the returned preds are the last query's, all heads
+        a3, _ = fused.approx_surface(net, pts.clone().requires_grad_(True), 3, q, df_type)
+        b3, _ = plain.approx_surface(net, pts.clone().requires_grad_(True), 3, q, df_type)
+        close = ((a3 - b3).norm(dim=-1) < 1e-3).float().mean().item()
+        assert close > 0.97, close
