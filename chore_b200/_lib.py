@@ -58,7 +58,7 @@ SIGNATURES = {
     "chore_landmarks_bwd": (_I, [_P, _P, _I, _P, _I, _P]),
     "chore_fit_workspace_floats": (C.c_size_t, [_I, _I]),
     "chore_fit_smpl_field_grads": (_I, [_P, _P, _P, _P, _I, _I, _F, _F, _P, _P, _P, _P, _P]),
-    "chore_fit_landmark_grads": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _F, _F, C.POINTER(C.c_float), _P, _P, _P]),
+    "chore_fit_landmark_grads": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _F, _F, C.POINTER(C.c_float), _P, _P, _P, _P]),
     "chore_fit_pose_prior_grads": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _P, _P, _P, _P]),
     "chore_fit_obj_field_grads": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P]),
     "chore_add_rowvec": (_I, [_P, _P, _P, _I, _I, _F, _P]),
@@ -302,13 +302,14 @@ class Handle:
                                                             g_df.data_ptr(), g_parts.data_ptr(), loss.data_ptr(), ws.data_ptr(), _stream()))
         return g_df, g_parts
 
-    def fit_landmark_grads(self, lm, kpts, crop_center, n_joints: int, z0: float, cz: float, cj: float, cam, loss):
-        check_cuda(lm, kpts, crop_center, loss)
+    def fit_landmark_grads(self, lm, kpts, crop_center, n_joints: int, z0: float, cz: float, cj: float, cam, loss, ws):
+        check_cuda(lm, kpts, crop_center, loss, ws)
         g_lm = torch.empty_like(lm)
         cam_c = (C.c_float * 6)(*[float(x) for x in cam])
         with torch.cuda.device(self.device):
             self._check(self.lib.chore_fit_landmark_grads(self.h, lm.data_ptr(), _ptr(kpts), crop_center.data_ptr(), lm.shape[0], lm.shape[1],
-                                                          n_joints, z0, cz, cj, cam_c, g_lm.data_ptr(), loss.data_ptr(), _stream()))
+                                                          n_joints, z0, cz, cj, cam_c, g_lm.data_ptr(), loss.data_ptr(), ws.data_ptr(),
+                                                          _stream()))
         return g_lm
 
     def fit_pose_prior_grads(self, pose, pose_init, priors, cb: float, ch: float, cp: float, g_pose, loss, ws) -> None:

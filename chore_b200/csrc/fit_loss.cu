@@ -79,7 +79,7 @@ __global__ void fit_sum_partials_kernel(const float *__restrict__ partials, int 
 struct CamConsts { float fx, fy, cx, cy, half_crop, scale; };
 // one thread per (b, landmark); smplz on body25 joint 8, j2d on the first nJ landmarks
 __global__ void fit_landmark_kernel(const float *__restrict__ lm, const float *__restrict__ kpts, const float *__restrict__ cc, int B, int L,
-                                    int nJ, float z0, float cz, float cj, CamConsts cam, float *__restrict__ g_lm, float *__restrict__ loss) {
+                                    int nJ, float z0, float cz, float cj, CamConsts cam, float *__restrict__ g_lm, float *__restrict__ partials) {
     __shared__ float red[32];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float l = 0.f;
@@ -100,8 +100,8 @@ __global__ void fit_landmark_kernel(const float *__restrict__ lm, const float *_
         }
         g_lm[(size_t)i * 3] = gx; g_lm[(size_t)i * 3 + 1] = gy; g_lm[(size_t)i * 3 + 2] = gz;
     }
-    const float t = block_sum(l, red);          // single block (B * L <= 1024 checked by the caller)
-    if (threadIdx.x == 0) loss[0] += t;
+    const float t = block_sum(l, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = t;
 }
 
 // ---- SMPL step: pose priors + initial-pose term ------------------------------------------------------------------
@@ -301,13 +301,15 @@ extern "C" int chore_fit_smpl_field_grads(chore_handle *h, const float *df, cons
 
 extern "C" int chore_fit_landmark_grads(chore_handle *h, const float *landmarks, const float *body_kpts, const float *crop_center, int B, int L,
                                         int n_joints, float z0, float cz, float cj, const float cam[6], float *g_landmarks, float *loss,
-                                        void *stream) {
-    CHORE_CHECK(h && landmarks && crop_center && cam && g_landmarks && loss && B > 0 && L > 8, "bad arguments");
-    CHORE_CHECK(B * L <= 1024 && n_joints <= L, "landmark count %d x %d exceeds one block", B, L);
+                                        float *workspace, void *stream) {
+    CHORE_CHECK(h && landmarks && crop_center && cam && g_landmarks && loss && workspace && B > 0 && L > 8 && n_joints <= L, "bad arguments");
     CamConsts c{cam[0], cam[1], cam[2], cam[3], cam[4], cam[5]};
-    const int threads = ((B * L + 31) / 32) * 32;
-    CHORE_LAUNCH(fit_landmark_kernel, 1, threads, 0, static_cast<cudaStream_t>(stream), landmarks, body_kpts, crop_center, B, L, n_joints, z0,
-                 cz, cj, c, g_landmarks, loss);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int blocks = (B * L + kRedThreads - 1) / kRedThreads;
+    CHORE_CHECK(blocks <= 256, "too many landmarks (%d x %d)", B, L);
+    CHORE_LAUNCH(fit_landmark_kernel, blocks, kRedThreads, 0, st, landmarks, body_kpts, crop_center, B, L, n_joints, z0, cz, cj, c,
+                 g_landmarks, workspace);
+    CHORE_LAUNCH(fit_sum_partials_kernel, 1, 32, 0, st, workspace, blocks, loss);
     return CHORE_OK;
 }
 

@@ -124,10 +124,13 @@ __device__ __forceinline__ TapsTc make_taps_tc(float nx, float ny, int H, int W)
 // one-point-at-a-time loop paid one full L2 round trip per point and left the MMA warp waiting on a_full).
 // Arithmetic is unchanged: v = sum_k tap_k * w_k in tap order nw, ne, sw, se, invalid taps contribute exactly 0.
 constexpr int kGatherBatch = 4;
-__device__ __forceinline__ void gather_kblock(const float *__restrict__ base, int H, int W, int C, float my_nx, float my_ny,
-                                              int g, int half, int l16, uint8_t *hi, uint8_t *lo) {
+// ROWS = tile rows owned by the calling warp (32 with four gather warps, 16 with eight), BATCH = points in flight per half-warp.
+template <int ROWS, int BATCH>
+__device__ __forceinline__ void gather_kblock_t(const float *__restrict__ base, int H, int W, int C, float my_nx, float my_ny,
+                                                int g, int half, int l16, uint8_t *hi, uint8_t *lo) {
+    constexpr int kGatherBatch = BATCH;
 #pragma unroll 1
-    for (int it0 = 0; it0 < 16; it0 += kGatherBatch) {
+    for (int it0 = 0; it0 < ROWS / 2; it0 += kGatherBatch) {
         float4 v[kGatherBatch][4];
         float wgt[kGatherBatch][4];
 #pragma unroll
@@ -145,7 +148,7 @@ __device__ __forceinline__ void gather_kblock(const float *__restrict__ base, in
         }
 #pragma unroll
         for (int j = 0; j < kGatherBatch; ++j) {
-            const int r = g * 32 + (it0 + j) * 2 + half;
+            const int r = g * ROWS + (it0 + j) * 2 + half;
             float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -160,6 +163,11 @@ __device__ __forceinline__ void gather_kblock(const float *__restrict__ base, in
             *reinterpret_cast<uint2 *>(lo + off) = make_uint2(l01, l23);
         }
     }
+}
+
+__device__ __forceinline__ void gather_kblock(const float *__restrict__ base, int H, int W, int C, float my_nx, float my_ny,
+                                              int g, int half, int l16, uint8_t *hi, uint8_t *lo) {
+    gather_kblock_t<32, kGatherBatch>(base, H, W, C, my_nx, my_ny, g, half, l16, hi, lo);
 }
 
 }   // namespace

@@ -516,7 +516,8 @@ class FusedFitSteps:
             nJ = sm.regressors.sizes[0]
             kp = d["body_kpts"] if self.phase == "kpts" else None
             cam = (fit.fx_px, fit.fy_px, fit.cx_px, fit.cy_px, fit.crop_size / 2, fit.net_in_size / fit.crop_size)
-            g_lm = self.h_aux.fit_landmark_grads(lm, kp, self.cc, nJ, fit.z_0, self.W["smplz"] * k / B, self.W["j2d"] * k / (B * nJ), cam, loss)
+            g_lm = self.h_aux.fit_landmark_grads(lm, kp, self.cc, nJ, fit.z_0, self.W["smplz"] * k / B, self.W["j2d"] * k / (B * nJ), cam, loss,
+                                                 self.ws)
             hl.landmarks_bwd(g_lm, g_verts)          # g_verts += R^T g_lm
         g_pose, g_betas, g_trans, _ = self.h_lbs.lbs_bwd(pose, betas, trans, off, g_verts, None, False)
         if self.priors_dev is not None or self.pose_init is not None:

@@ -193,7 +193,7 @@ int chore_fit_smpl_field_grads(chore_handle *h, const float *df, const float *pa
  * net_in_size/crop_size}   (recon_fit_base.py:230-231, 653-676; model/camera.py:51-71) */
 int chore_fit_landmark_grads(chore_handle *h, const float *landmarks, const float *body_kpts,
                              const float *crop_center, int B, int L, int n_joints, float z0, float cz, float cj,
-                             const float cam[6], float *g_landmarks, float *loss, void *stream);
+                             const float cam[6], float *g_landmarks, float *loss, float *workspace, void *stream);
 /* cb * sum_b |(pose[3:66]-mean) P|^2 + ch * sum_b,hands |(pose[66:]-mean_h) P_h|^2 + cp * sum_b |pose[3:72]-pose_init|^2;
  * gradients are ADDED to g_pose (B,156).  Priors / pose_init may be NULL (term skipped)
  * (lib_smpl/th_smpl_prior.py:32-39, lib_smpl/th_hand_prior.py:69-78, recon_fit_behave.py:317-319) */
