@@ -89,26 +89,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// x = hi + lo, both fp16 (clamped to the fp16 range); packs two consecutive values
-__device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo) {
-    a = fminf(fmaxf(a, -65504.f), 65504.f);
-    b = fminf(fmaxf(b, -65504.f), 65504.f);
-    const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
-    const __half la = __float2half_rn(a - __half2float(ha)), lb = __float2half_rn(b - __half2float(hb));
-    hi = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
-    lo = (uint32_t)__half_as_ushort(la) | ((uint32_t)__half_as_ushort(lb) << 16);
+// two floats -> packed fp16x2 (a in the low half), round to nearest even, saturating to +-65504 instead of inf:
+// one F2FP.SATFINITE instruction replaces the clamp + two scalar conversions + pack
+__device__ __forceinline__ uint32_t cvt_f16x2_sat(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
 }
 
-// same for non-negative inputs (post-ReLU activations), with packed conversions
-__device__ __forceinline__ void split2_pos(float a, float b, uint32_t &hi, uint32_t &lo) {
-    a = fminf(a, 65504.f);
-    b = fminf(b, 65504.f);
-    const __half2 h = __floats2half2_rn(a, b);
-    const float2 back = __half22float2(h);
-    const __half2 l = __floats2half2_rn(a - back.x, b - back.y);
-    hi = *reinterpret_cast<const uint32_t *>(&h);
-    lo = *reinterpret_cast<const uint32_t *>(&l);
+// x = hi + lo, both fp16 (hi saturates at the fp16 range); packs two consecutive values.  For |x| <= 65504 this is
+// bit-identical to clamp -> __float2half_rn.
+__device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo) {
+    hi = cvt_f16x2_sat(a, b);
+    const float2 back = __half22float2(*reinterpret_cast<const __half2 *>(&hi));
+    lo = cvt_f16x2_sat(a - back.x, b - back.y);
 }
+
+// same for non-negative inputs (post-ReLU activations); kept as a separate name for the call sites
+__device__ __forceinline__ void split2_pos(float a, float b, uint32_t &hi, uint32_t &lo) { split2(a, b, hi, lo); }
 
 // byte offset of 16-byte chunk `c` (8 fp16) of row `r` inside a 128B-swizzled K-major panel
 __device__ __forceinline__ uint32_t sw128(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
