@@ -318,12 +318,14 @@ __global__ void __launch_bounds__(kThreads, 1) query_tc_kernel(const TcParams q)
 #pragma unroll
                             for (int c8 = 0; c8 < 4; ++c8) {     // 8 columns = one 16-byte chunk of fp16
                                 uint32_t hh[4], ll[4];
+                                const float4 bA = __ldg(reinterpret_cast<const float4 *>(bias + part * 32 + c8 * 8));
+                                const float4 bB = __ldg(reinterpret_cast<const float4 *>(bias + part * 32 + c8 * 8 + 4));
+                                const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
                                     const int c = c8 * 8 + j * 2;
-                                    const float2 bb = __ldg(reinterpret_cast<const float2 *>(bias + part * 32 + c));
-                                    const float a0 = fmaxf(__uint_as_float(v[c]) + bb.x, 0.f);
-                                    const float a1 = fmaxf(__uint_as_float(v[c + 1]) + bb.y, 0.f);
+                                    const float a0 = fmaxf(__uint_as_float(v[c]) + bb[j * 2], 0.f);
+                                    const float a1 = fmaxf(__uint_as_float(v[c + 1]) + bb[j * 2 + 1], 0.f);
                                     split2_pos(a0, a1, hh[j], ll[j]);
                                 }
                                 const uint32_t off = sw128(row, part * 4 + c8);
