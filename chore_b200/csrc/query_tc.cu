@@ -251,14 +251,15 @@ __global__ void __launch_bounds__(kThreads, 1) query_tc_kernel(const TcParams q)
             float my_x = 0.f, my_y = 0.f, my_z = 1.f, my_nx, my_ny;
             if (n0 + g * 32 + lane < q.n_count) load_point(q, b, n0 + g * 32 + lane, my_x, my_y, my_z);
             project_tc(my_x, my_y, my_z, ccx, ccy, my_nx, my_ny);
+            const LaneTaps tapsF = make_lane_taps(my_nx, my_ny, q.fh, q.fw, kFeatC), tapsS = make_lane_taps(my_nx, my_ny, 2 * q.fh, 2 * q.fw, kSkipC);
             for (int kb = 0; kb < kL1Blocks; ++kb, ++ablk) {
                 const int sa = ablk % kNA;
                 mbar_wait_t(&bars->a_empty[sa], ((ablk / kNA) & 1) ^ 1, DBG(6));
                 uint8_t *hi = ringA + (size_t)sa * kStageA, *lo = hi + kPanelBytes;
                 if (kb < 5) {
                     const bool is_feat = kb < 4;
-                    gather_kblock((is_feat ? F + kb * 64 : S) + l16 * 4, is_feat ? q.fh : 2 * q.fh, is_feat ? q.fw : 2 * q.fw,
-                                  is_feat ? kFeatC : kSkipC, my_nx, my_ny, g, half, l16, hi, lo);
+                    gather_kblock_p<32, kGatherBatch>((is_feat ? F + kb * 64 : S) + l16 * 4, (is_feat ? q.fw * kFeatC : 2 * q.fw * kSkipC),
+                                                      is_feat ? kFeatC : kSkipC, is_feat ? tapsF : tapsS, g, half, l16, hi, lo);
                 } else {
                     // z_feat = [x, y, z - 2.2] (model/chore.py:128-129) + 13 zero channels: one k-step, lane = row
                     const int r = g * 32 + lane;
@@ -547,14 +548,15 @@ __global__ void __launch_bounds__(kThreads, 1) query_bwd_tc_kernel(const TcParam
             float my_x = 0.f, my_y = 0.f, my_z = 1.f, my_nx, my_ny;
             if (n0 + g * 32 + lane < q.n_count) load_point(q, b, n0 + g * 32 + lane, my_x, my_y, my_z);
             project_tc(my_x, my_y, my_z, ccx, ccy, my_nx, my_ny);
+            const LaneTaps tapsF = make_lane_taps(my_nx, my_ny, q.fh, q.fw, kFeatC), tapsS = make_lane_taps(my_nx, my_ny, 2 * q.fh, 2 * q.fw, kSkipC);
             for (int kb = 0; kb < kL1Blocks; ++kb, ++ablk) {
                 const int sa = ablk % 2;
                 mbar_wait(&bars->a_empty[sa], ((ablk / 2) & 1) ^ 1);
                 uint8_t *hi = ringA + (size_t)sa * kStageA, *lo = hi + kPanelBytes;
                 if (kb < 5) {
                     const bool is_feat = kb < 4;
-                    gather_kblock((is_feat ? F + kb * 64 : S) + l16 * 4, is_feat ? q.fh : 2 * q.fh, is_feat ? q.fw : 2 * q.fw,
-                                  is_feat ? kFeatC : kSkipC, my_nx, my_ny, g, half, l16, hi, lo);
+                    gather_kblock_p<32, kGatherBatch>((is_feat ? F + kb * 64 : S) + l16 * 4, (is_feat ? q.fw * kFeatC : 2 * q.fw * kSkipC),
+                                                      is_feat ? kFeatC : kSkipC, is_feat ? tapsF : tapsS, g, half, l16, hi, lo);
                 } else {
                     const int r = g * 32 + lane;
                     uint32_t h01, l01, h23, l23;

@@ -165,6 +165,60 @@ __device__ __forceinline__ void gather_kblock_t(const float *__restrict__ base, 
     }
 }
 
+// ---- variant with the taps evaluated once per tile and map --------------------------------------------------------
+// Lane L keeps, for the point it projects, the packed tap descriptor of a map: element offset of tap (y0, x0) from the
+// map base -- a multiple of C >= 64, so the 4 validity bits ride in its low bits -- and the two fractional weights.
+// gather_kblock_p broadcasts them with 3 shuffles per point instead of re-deriving them (2 shuffles + ~45 ALU ops).
+struct LaneTaps { int off_valid; float wx, wy; };
+__device__ __forceinline__ LaneTaps make_lane_taps(float nx, float ny, int H, int W, int C) {
+    const TapsTc t = make_taps_tc(nx, ny, H, W);
+    const float ix = __fmul_rn(__fadd_rn(nx, 1.0f), 0.5f * (float)(W - 1)), iy = __fmul_rn(__fadd_rn(ny, 1.0f), 0.5f * (float)(H - 1));
+    LaneTaps l;
+    l.off_valid = t.valid ? ((t.y0 * W + t.x0) * C) | (int)t.valid : 0;     // two's complement: the OR also works for negative offsets
+    l.wx = t.valid ? ix - floorf(ix) : 0.f;
+    l.wy = t.valid ? iy - floorf(iy) : 0.f;
+    return l;
+}
+template <int ROWS, int BATCH>
+__device__ __forceinline__ void gather_kblock_p(const float *__restrict__ base, int rowC, int C, const LaneTaps mine,
+                                                int g, int half, int l16, uint8_t *hi, uint8_t *lo) {
+#pragma unroll 1
+    for (int it0 = 0; it0 < ROWS / 2; it0 += BATCH) {
+        float4 v[BATCH][4];
+        float wx[BATCH], wy[BATCH];
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j) {
+            const int src = (it0 + j) * 2 + half;
+            const int ov = __shfl_sync(0xffffffffu, mine.off_valid, src);
+            wx[j] = __shfl_sync(0xffffffffu, mine.wx, src);
+            wy[j] = __shfl_sync(0xffffffffu, mine.wy, src);
+            const float *p = base + (ov & ~15);
+            v[j][0] = (ov & 1) ? __ldg(reinterpret_cast<const float4 *>(p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[j][1] = (ov & 2) ? __ldg(reinterpret_cast<const float4 *>(p + C)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[j][2] = (ov & 4) ? __ldg(reinterpret_cast<const float4 *>(p + rowC)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[j][3] = (ov & 8) ? __ldg(reinterpret_cast<const float4 *>(p + rowC + C)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j) {
+            const int r = g * ROWS + (it0 + j) * 2 + half;
+            const float ux = 1.f - wx[j], uy = 1.f - wy[j];
+            const float w[4] = {uy * ux, uy * wx[j], wy[j] * ux, wy[j] * wx[j]};
+            float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                v0 = fmaf(v[j][k].x, w[k], v0); v1 = fmaf(v[j][k].y, w[k], v1);
+                v2 = fmaf(v[j][k].z, w[k], v2); v3 = fmaf(v[j][k].w, w[k], v3);
+            }
+            uint32_t h01, l01, h23, l23;
+            split2(v0, v1, h01, l01);
+            split2(v2, v3, h23, l23);
+            const uint32_t off = sw128(r, l16 >> 1) + (l16 & 1) * 8;
+            *reinterpret_cast<uint2 *>(hi + off) = make_uint2(h01, h23);
+            *reinterpret_cast<uint2 *>(lo + off) = make_uint2(l01, l23);
+        }
+    }
+}
+
 __device__ __forceinline__ void gather_kblock(const float *__restrict__ base, int H, int W, int C, float my_nx, float my_ny,
                                               int g, int half, int l16, uint8_t *hi, uint8_t *lo) {
     gather_kblock_t<32, kGatherBatch>(base, H, W, C, my_nx, my_ny, g, half, l16, hi, lo);
