@@ -42,7 +42,14 @@ struct Bars {
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 1) query_tc_kernel(const TcParams q) {
+// 15 warps: warp 14 is a second MMA issuer.  The thread that issues a tcgen05.mma is held until the tensor pipe takes
+// the instruction, so whatever it does between two MMAs (barrier waits, fences, descriptor moves, commits) is added to
+// the math time instead of overlapping it (profiles/mma_microbench_r1.txt).  With two issuers -- warp 1 owns heads 0 and 2,
+// warp 14 heads 1 and 3, same global order of weight panels and activation blocks -- one prepares its next step while the
+// other's MMAs execute.
+constexpr int kIssuerB = 14;
+constexpr int kThreadsFwd = 15 * 32;
+__global__ void __launch_bounds__(kThreadsFwd, 1) query_tc_kernel(const TcParams q) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *ringA = smem;                                      // [kNA][hi 16K | lo 16K]
@@ -58,7 +65,8 @@ __global__ void __launch_bounds__(kThreads, 1) query_tc_kernel(const TcParams q)
 #define DBG(i) (dbg_on ? &dbg_local[i] : nullptr)
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kNA; ++i) { mbar_init(&bars->a_full[i], 4); mbar_init(&bars->a_empty[i], 1); }
+        const int n_issuers = ((q.head_mask & 5u) != 0) + ((q.head_mask & 10u) != 0);     // an A stage is released by every issuer that reads it
+        for (int i = 0; i < kNA; ++i) { mbar_init(&bars->a_full[i], 4); mbar_init(&bars->a_empty[i], n_issuers); }
         for (int i = 0; i < kNW; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
         for (int i = 0; i < kNACT; ++i) { mbar_init(&bars->act_full[i], 4); mbar_init(&bars->act_empty[i], 1); }
         for (int i = 0; i < 4; ++i) { mbar_init(&bars->tm_full[i], 1); mbar_init(&bars->tm_empty[i], 4); }
@@ -98,10 +106,13 @@ __global__ void __launch_bounds__(kThreads, 1) query_tc_kernel(const TcParams q)
                 ++u;
             }
         }
-    } else if (warp == 1) {
-        // =============================== MMA issuer ===============================
+    } else if (warp == 1 || warp == kIssuerB) {
+        // =============================== MMA issuers ===============================
         // All 32 lanes run the loop converged so that every operand is warp-uniform; only the tcgen05
-        // instructions themselves are predicated on one elected lane.
+        // instructions themselves are predicated on one elected lane.  Warp 1 issues for heads 0 and 2, warp 14 for heads
+        // 1 and 3 (consecutive steps alternate between the issuers); both walk the same global sequence of weight panels /
+        // activation blocks and skip the other's entries.
+        const unsigned my_heads = q.head_mask & (warp == 1 ? 5u : 10u);
         constexpr uint32_t idesc = make_idesc(kTileM, 128), idesc16 = make_idesc(kTileM, 16);
         const uint32_t ringA_lo = desc_lo(smem_u32(ringA)), ringAct_lo = desc_lo(smem_u32(ringAct)), ringW_lo = desc_lo(smem_u32(ringW));
         constexpr uint32_t kStageLo = kStageA >> 4, kPanelLo = kPanelBytes >> 4;
@@ -109,8 +120,8 @@ __global__ void __launch_bounds__(kThreads, 1) query_tc_kernel(const TcParams q)
         uint32_t ablk = 0;     // A ring block counter
         uint32_t actblk = 0;   // activation ring block counter
         uint32_t tile_i = 0;
-        const int last_head = 31 - __clz((int)(q.head_mask & 15u));     // the A stage is released after the last active head
-        for (long long tile = first_tile; tile < q.total_tiles; tile += tile_stride, ++tile_i) {
+        const int last_head = 31 - __clz((int)my_heads);     // this issuer releases the A stage after its last active head
+        for (long long tile = first_tile; my_heads != 0 && tile < q.total_tiles; tile += tile_stride, ++tile_i) {
             // ---- layer 1: 6 k-blocks x 4 heads, all four accumulators live ----
             for (int kb = 0; kb < kL1Blocks; ++kb, ++ablk) {
                 const int sa = ablk % kNA;
@@ -121,6 +132,7 @@ __global__ void __launch_bounds__(kThreads, 1) query_tc_kernel(const TcParams q)
 #pragma unroll 1
                 for (int h = 0; h < 4; ++h) {
                     if (!((q.head_mask >> h) & 1)) continue;
+                    if (!((my_heads >> h) & 1)) { u += 2; continue; }        // the other issuer's panels
                     if (kb == 0) {   // accumulator of head h must have been drained (previous tile)
                         mbar_wait_t(&bars->tm_empty[h], (tile_i & 1) ^ 1, DBG(2));
                         tc_fence_after();
@@ -166,6 +178,7 @@ __global__ void __launch_bounds__(kThreads, 1) query_tc_kernel(const TcParams q)
 #pragma unroll 1
                 for (int h = 0; h < 4; ++h) {
                     if (!((q.head_mask >> h) & 1)) continue;
+                    if (!((my_heads >> h) & 1)) { actblk += 2; u += layer < 3 ? 4 : 1; continue; }     // the other issuer's head
                     const uint32_t d = tmem_base + h * 128;
                     // both activation blocks must be complete before the accumulator is overwritten
                     const uint32_t b0 = actblk, b1 = actblk + 1;
@@ -982,7 +995,7 @@ int query_tc_launch(chore_handle *h, const float *feat, const float *skip, int f
         CHORE_CUDA(cudaMemsetAsync(dbg, 0, (size_t)grid * 16 * sizeof(unsigned long long), st));
         q.dbg = dbg;
     }
-    CHORE_LAUNCH(query_tc_kernel, (unsigned)grid, kThreads, kSmemBytes, st, q);
+    CHORE_LAUNCH(query_tc_kernel, (unsigned)grid, kThreadsFwd, kSmemBytes, st, q);
     if (trace) {   // debugging aid: synchronous, prints the mean wait cycles per role
         std::vector<unsigned long long> hbuf((size_t)grid * 16);
         CHORE_CUDA(cudaMemcpyAsync(hbuf.data(), dbg, hbuf.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
