@@ -568,3 +568,55 @@ def smpl_full_losses(sd, feat, tmpx, crop_center, model: Dict[str, Tensor], pose
         l2 = F.mse_loss(proj[:, :, :2], body_kpts[:, :, :2], reduction="none")
         out["j2d"] = torch.mean(torch.sum(l2, dim=-1) * body_kpts[:, :, 2])
     return out
+
+
+# ----------------------------------------------------------------------------------------
+# independent plain-numpy restatement of the LBS (float64), for small batches: guards the torch restatement above
+# against misread tensor semantics (smpl_layer.py:72-175, tensutils.py:6-53, rodrigues_layer.py:13-52)
+# ----------------------------------------------------------------------------------------
+def lbs_numpy(model: Dict[str, Tensor], pose: np.ndarray, betas: np.ndarray, trans: np.ndarray,
+              offsets: np.ndarray | None = None):
+    vt = model["v_template"].double().numpy().reshape(-1, 3)
+    sdirs = model["shapedirs"].double().numpy()            # (V,3,nb)
+    pdirs = model["posedirs"].double().numpy()             # (V,3,(J-1)*9)
+    jreg = model["J_regressor"].double().numpy()           # (J,V)
+    wts = model["weights"].double().numpy()                # (V,J)
+    parents = [int(p) for p in model["parents"]]
+    J = wts.shape[1]
+    out_v, out_j = [], []
+    for b in range(pose.shape[0]):
+        R = []
+        for j in range(J):
+            r = pose[b, 3 * j:3 * j + 3].astype(np.float64)
+            ang = np.linalg.norm(r + 1e-8)
+            n = r / ang
+            q = np.concatenate([[np.cos(ang / 2)], np.sin(ang / 2) * n])
+            q = q / np.linalg.norm(q)
+            w, x, y, z = q
+            R.append(np.array([[w * w + x * x - y * y - z * z, 2 * x * y - 2 * w * z, 2 * w * y + 2 * x * z],
+                               [2 * w * z + 2 * x * y, w * w - x * x + y * y - z * z, 2 * y * z - 2 * w * x],
+                               [2 * x * z - 2 * w * y, 2 * w * x + 2 * y * z, w * w - x * x - y * y + z * z]]))
+        v_shaped = vt + sdirs @ betas[b].astype(np.float64)
+        jnt = jreg @ v_shaped
+        pmap = np.concatenate([(R[j] - np.eye(3)).reshape(-1) for j in range(1, J)])
+        v_posed = v_shaped + pdirs @ pmap
+        if offsets is not None:
+            v_posed = v_posed + offsets[b]
+        G = [None] * J
+        for j in range(J):
+            T = np.eye(4)
+            T[:3, :3] = R[j]
+            T[:3, 3] = jnt[j] - (jnt[parents[j]] if j > 0 else 0.0)
+            G[j] = T if j == 0 else G[parents[j]] @ T
+        A = []
+        for j in range(J):
+            M = G[j].copy()
+            M[:3, 3] -= G[j][:3, :3] @ jnt[j]
+            A.append(M)
+        A = np.stack(A)                                      # (J,4,4)
+        Tv = np.einsum("vj,jab->vab", wts, A)
+        vh = np.concatenate([v_posed, np.ones((v_posed.shape[0], 1))], 1)
+        verts = np.einsum("vab,vb->va", Tv, vh)[:, :3] + trans[b]
+        out_v.append(verts)
+        out_j.append(np.stack([g[:3, 3] for g in G]) + trans[b])
+    return np.stack(out_v), np.stack(out_j)

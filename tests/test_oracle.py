@@ -179,3 +179,13 @@ def test_fit_smpl_full_vs_golden(sd):
     verts = O.lbs_forward(buf, T(g["pose"]), T(g["betas"]), T(g["trans"]))[0]
     for r, name in zip(regs_t, ("J", "face", "hands")):
         assert rel_err(torch.matmul(r, verts), g[name]) < TOL, name
+
+
+def test_lbs_numpy_restatement():
+    """Second, torch-free LBS (float64) agrees with the torch restatement and with the reference's own run."""
+    g = load_golden("lbs.npz")
+    buf = O.make_smplh_buffers(int(g["buffers_seed"]))
+    v, j = O.lbs_numpy(buf, g["pose"], g["betas"], g["trans"], g["offsets"])
+    assert rel_err(T(v), g["verts"]) < 2e-5 and rel_err(T(j), g["jtr"]) < 2e-5
+    vt, jt, _, _ = O.lbs_forward(buf, T(g["pose"]), T(g["betas"]), T(g["trans"]), T(g["offsets"]))
+    assert rel_err(T(v), vt) < 2e-5 and rel_err(T(j), jt) < 2e-5
