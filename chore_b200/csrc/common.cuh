@@ -66,7 +66,8 @@ struct MlpWeights {
 
 // ---- encoder weights ------------------------------------------------------------------------------
 struct ConvW {
-    unsigned char *wtc = nullptr;   // tensor-core path: [tap][kb][hi|lo] fp16 panels (conv_tc.cu)
+    unsigned char *wtc = nullptr;   // first tensor-core path: [tap][kb][hi|lo] fp16 panels (conv_tc.cu), packed on demand
+    unsigned char *whx = nullptr;   // halo/transform path: [kb][tap][hi|lo] fp16 panels (conv_hx.cu)
     float *w = nullptr;     // [kh][kw][cin][cout]  (HWIO)
     float *bias = nullptr;  // [cout] or null
     int kh = 0, kw = 0, cin = 0, cout = 0;
@@ -122,7 +123,10 @@ struct chore_handle {
     void *lbs_ws = nullptr;      // LBS / rigid intermediates (own buffer: may interleave with encode)
     size_t lbs_ws_bytes = 0;
     std::vector<void *> owned;   // device allocations released by chore_destroy
+    bool hx_configured = false;  // per-handle (= per-device) kernel attributes set (conv_hx.cu)
+    struct EncoderPlan *enc_plan = nullptr;   // cached CUDA graphs of chore_encode (encoder_hx.cu)
 };
+void encoder_plan_destroy(chore_handle *h);
 
 int chore_ws_reserve(chore_handle *h, size_t bytes);    // (re)allocates h->ws
 int chore_ws2_reserve(chore_handle *h, size_t bytes);   // (re)allocates h->ws2
@@ -162,6 +166,32 @@ struct ConvTcArgs {
 bool encoder_use_tensor_cores();   // CHORE_B200_ENCODER=simt selects the fp32 SIMT convolutions
 int conv_tc_pack_weights(chore_handle *h, const float *w, int cout, int cin, int kh, int kw, unsigned char **dev);
 int conv_tc_launch(const ConvTcArgs &a, cudaStream_t st);
+
+// halo/transform tensor-core convolutions with fused GroupNorm prologue and statistics epilogue (conv_hx.cu)
+struct ConvHxArgs {
+    const float *in; int ld_in, off_in, Cin;     // fp32 NHWC input, channels [off_in, off_in + Cin) of rows of ld_in
+    int B, H, W, KS, N;                          // N = Cout
+    const unsigned char *w;                      // ConvW::whx
+    const float *bias;                           // [N] or null
+    const double *gn_in;                         // [B][32][2] sums of the input (GroupNorm(32, Cin)), null = identity
+    const float *gamma, *beta; int relu;
+    float *out; int ld_out, off_out;             // out = conv (+bias) (+res)
+    const float *res; int ld_res, off_res;       // optional residual (may alias out)
+    float *raw; int ld_raw, off_raw;             // optional copy of conv (+bias) without the residual
+    double *st_raw; int cpg_raw;                 // optional statistics of raw / out: [B][32][2], channels per group
+    double *st_out; int cpg_out;
+};
+int conv_hx_pack_weights(chore_handle *h, const float *w, int cout, int cin, int kh, int kw, unsigned char **dev);
+int conv_hx_configure(chore_handle *h);   // per-device kernel attributes (idempotent)
+struct ConvHxPlan {
+    int tiles, n_splits, k_splits;
+    size_t part_floats;      // fp32 scratch for the partial tiles of a K split (0 = none)
+    int counters;            // zero-initialised ints the launch needs (0 = none)
+};
+int conv_hx_plan(const chore_handle *h, const ConvHxArgs &a, ConvHxPlan *plan);
+int conv_hx_launch(chore_handle *h, const ConvHxArgs &a, const ConvHxPlan &plan, float *part, int *part_cnt, cudaStream_t st);
+int encode_hx(chore_handle *h, const float *images, int B, int H, int W, float *feat, float *skip, float *normx, cudaStream_t st);
+const char *encoder_mode();   // CHORE_B200_ENCODER: "hx" (default), "tc1" (first tensor-core path), "simt"
 
 // implemented per translation unit
 int query_load_weights(chore_handle *h, const std::map<std::string, const chore_tensor_desc *> &t);

@@ -242,13 +242,18 @@ int make_map(CUtensorMap *map, const void *base, int Cp, int W, int H, int B) {
 
 }   // namespace
 
-bool encoder_use_tensor_cores() {
-    static const bool simt = [] {
+// CHORE_B200_ENCODER selects the encoder implementation: "hx" (default: conv_hx.cu + encoder_hx.cu), "tc1" (the first
+// tensor-core path of this file, kept for A/B comparisons) or "simt" (fp32 CUDA-core convolutions, cross-check only)
+const char *encoder_mode() {
+    static const char *mode = [] {
         const char *e = getenv("CHORE_B200_ENCODER");
-        return e != nullptr && strcmp(e, "simt") == 0;
+        if (e != nullptr && strcmp(e, "simt") == 0) return "simt";
+        if (e != nullptr && strcmp(e, "tc1") == 0) return "tc1";
+        return "hx";
     }();
-    return !simt;
+    return mode;
 }
+bool encoder_use_tensor_cores() { return strcmp(encoder_mode(), "tc1") == 0; }
 
 // weights (Cout, Cin, kh, kw) fp32 -> [tap][kb][hi|lo] panels of Cout rows x 64 k fp16, 128B swizzled.
 // Packed on the device: the host-side fp16 conversions of 18 M parameters took tens of seconds.

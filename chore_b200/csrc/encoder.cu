@@ -705,8 +705,14 @@ int encoder_load_weights(chore_handle *h, const std::map<std::string, const chor
             CHORE_CUDA(cudaMemcpy(dev, dst.data(), n * sizeof(float), cudaMemcpyHostToDevice));
             ConvW &w = e.conv[base];
             w.w = dev; w.kh = kh; w.kw = kw; w.cin = ci; w.cout = co;
-            if (base != "image_filter.conv1" && (kh == 1 || kh == 3) && co % 32 == 0 && co <= 256)
-                if (int rc = conv_tc_pack_weights(h, src.data(), co, ci, kh, kw, &w.wtc)) return rc;
+            if (base != "image_filter.conv1" && (kh == 1 || kh == 3) && co % 32 == 0 && co <= 256) {
+                const std::string mode = encoder_mode();
+                if (mode == "hx") {
+                    if (int rc = conv_hx_pack_weights(h, src.data(), co, ci, kh, kw, &w.whx)) return rc;
+                } else if (mode == "tc1") {
+                    if (int rc = conv_tc_pack_weights(h, src.data(), co, ci, kh, kw, &w.wtc)) return rc;
+                }
+            }
         } else if (d->ndim == 1) {
             if (int rc = chore_dev_alloc(h, reinterpret_cast<void **>(&dev), n * sizeof(float))) return rc;
             CHORE_CUDA(cudaMemcpy(dev, src.data(), n * sizeof(float), cudaMemcpyHostToDevice));
@@ -732,6 +738,7 @@ extern "C" int chore_encode(chore_handle *h, const float *images, int B, int H, 
         chore_set_error("encoder weights not loaded (chore_load_weights)");
         return CHORE_ERR_NO_WEIGHTS;
     }
+    if (strcmp(encoder_mode(), "hx") == 0) return encode_hx(h, images, B, H, W, feat, skip, normx, static_cast<cudaStream_t>(stream));
     Ctx dry{};
     dry.h = h; dry.B = B; dry.dry = true; dry.st = nullptr;
     try {

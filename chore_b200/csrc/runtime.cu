@@ -63,6 +63,7 @@ extern "C" void chore_destroy(chore_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
+    encoder_plan_destroy(h);
     for (void *p : h->owned) cudaFree(p);
     if (h->ws) cudaFree(h->ws);
     if (h->ws2) cudaFree(h->ws2);
