@@ -26,7 +26,7 @@ class ChoreError(RuntimeError):
 
 class AdamEntry(C.Structure):
     _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
-                ("rows", C.c_int), ("cols", C.c_int), ("grad_ld", C.c_int)]
+                ("grad_acc", C.c_void_p), ("rows", C.c_int), ("cols", C.c_int), ("grad_ld", C.c_int)]
 
 
 class TensorDesc(C.Structure):
@@ -64,7 +64,7 @@ SIGNATURES = {
     "chore_add_rowvec": (_I, [_P, _P, _P, _I, _I, _F, _P]),
     "chore_surface_clamp_grad": (_I, [_P, _P, _I, _F, _I, _I, _P, _P]),
     "chore_surface_step": (_I, [_P, _P, _P, _P, _I, _F, _I, _I, _P, _P]),
-    "chore_adam_step": (_I, [_P, C.POINTER(AdamEntry), _I, _F, _F, _F, _F, _P, _P]),
+    "chore_adam_step": (_I, [_P, C.POINTER(AdamEntry), _I, _F, _F, _F, _F, _P, _P, _P, _P]),
     "chore_rigid_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P]),
     "chore_rigid_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "chore_project_so3": (_I, [_P, _P, _I, _P, _P]),
@@ -353,9 +353,10 @@ class Handle:
                                                     points.shape[0], points.shape[1], out.data_ptr(), _stream()))
         return out
 
-    def adam_step(self, entries, n: int, lr: float, beta1: float, beta2: float, eps: float, step) -> None:
+    def adam_step(self, entries, n: int, lr: float, beta1: float, beta2: float, eps: float, step, gscale=None, loss=None) -> None:
         with torch.cuda.device(self.device):
-            self._check(self.lib.chore_adam_step(self.h, entries, n, lr, beta1, beta2, eps, step.data_ptr(), _stream()))
+            self._check(self.lib.chore_adam_step(self.h, entries, n, lr, beta1, beta2, eps, step.data_ptr(), _ptr(gscale), _ptr(loss),
+                                                 _stream()))
 
     # ---- rigid object ------------------------------------------------------------------------
     def rigid_fwd(self, verts, R, t, s):

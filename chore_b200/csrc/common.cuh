@@ -30,6 +30,19 @@ extern std::atomic<uint64_t> g_launch_count;
         }                                                                                    \
     } while (0)
 
+// cudaFuncSetAttribute is per device (context): run `call` once per device of this process, not once per process.
+// The bit test / set is atomic; two threads racing on the same device at worst both make the (idempotent) call.
+#define CHORE_ONCE_PER_DEVICE(call)                                                          \
+    do {                                                                                     \
+        static std::atomic<uint64_t> done_{0};                                               \
+        int dev_ = 0;                                                                        \
+        cudaGetDevice(&dev_);                                                                \
+        if (!((done_.load(std::memory_order_acquire) >> (dev_ & 63)) & 1ull)) {              \
+            CHORE_CUDA(call);                                                                \
+            done_.fetch_or(1ull << (dev_ & 63), std::memory_order_release);                  \
+        }                                                                                    \
+    } while (0)
+
 // every kernel launch goes through this so chore_launch_count() is exact
 #define CHORE_LAUNCH(kernel, grid, block, smem, stream, ...)                                 \
     do {                                                                                     \
@@ -37,6 +50,32 @@ extern std::atomic<uint64_t> g_launch_count;
         g_launch_count.fetch_add(1, std::memory_order_relaxed);                              \
         CHORE_CUDA(cudaGetLastError());                                                      \
     } while (0)
+
+// Programmatic dependent launch: the kernel may start while its predecessor in the stream drains (its CTAs then block
+// in griddepcontrol.wait -- chore_pdl_wait() -- until the predecessor's memory is visible).  Every kernel launched this
+// way MUST call chore_pdl_wait() before it reads or writes anything a predecessor touches and before it exits.
+// Opt-in with CHORE_B200_PDL=1 (ordinary stream order otherwise: replayed from a CUDA graph the encoder gained nothing).
+bool chore_pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t chore_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = chore_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define CHORE_LAUNCH_PDL(kernel, grid, block, smem, stream, ...)                             \
+    do {                                                                                     \
+        g_launch_count.fetch_add(1, std::memory_order_relaxed);                              \
+        CHORE_CUDA(chore_launch_pdl(kernel, (grid), (block), (smem), (stream), __VA_ARGS__)); \
+    } while (0)
+#ifdef __CUDACC__
+__device__ __forceinline__ void chore_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void chore_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
 
 // ---- constants of the chore-release configuration ------------------------------------------
 constexpr int kFeatC = CHORE_FEAT_CH;     // 256

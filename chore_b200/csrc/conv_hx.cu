@@ -41,7 +41,7 @@ struct HxCtl {
     uint32_t tmem_base, pad[3];
     uint2 dummy[4];                                    // target of the stores of halo slots beyond the tile
     float sc[256], sh[256];
-    float stp[4][2][kGroups * 2];                      // per epilogue warp / set (0 = raw, 1 = out): this item's sums
+    float stp[12][2][kGroups * 2];                     // per worker warp (3 per TMEM lane quarter) / set (0 = raw, 1 = out): this item's sums
 };
 
 struct HxParams {
@@ -49,7 +49,7 @@ struct HxParams {
     int n_splits, k_splits, kt_per, Ns, tiles_x, tiles_y, n_items, kblocks, n_slots;
     uint32_t halo_plane, w_slot;
     double inv_n;          // 1 / (H * W * channels per group of the input)
-    float *part;           // K split: [(tile, n slice)][k_splits - 1][128][Ns] fp32 partial tiles
+    float *part;           // K split: [(tile, n slice)][k_splits][128][Ns] fp32 partial tiles (a part parks the chunks it does not own)
     int *part_cnt;         // K split: arrivals per (tile, n slice), zeroed before the launch
     long long *trace;      // debugging: 32 clock64 stamps of CTA 0 (null = off)
 };
@@ -155,16 +155,11 @@ __global__ void __launch_bounds__(kThreadsHx, 1) conv_hx_kernel(const HxParams p
     const int tiles_per_img = p.tiles_x * p.tiles_y;
     const int nk = p.n_splits * p.k_splits;
 
-    // the GroupNorm table inputs of the first item travel while the CTA sets itself up
+    chore_pdl_launch_dependents();                          // the next kernel of the stream may start its own set-up
     const int tx = threadIdx.x - kFirstTxWarp * 32;         // transform thread index (0..255) or negative
     double st_s = 0.0, st_q = 0.0;
     float gam = 1.f, bet = 0.f;
-    if (tx >= 0 && tx < a.Cin && a.gn_in != nullptr && (int)blockIdx.x < p.n_items) {
-        const int b0 = ((int)blockIdx.x / nk) / tiles_per_img, g = tx / (a.Cin / kGroups);
-        st_s = __ldcg(a.gn_in + (size_t)b0 * kGroups * 2 + g * 2);
-        st_q = __ldcg(a.gn_in + (size_t)b0 * kGroups * 2 + g * 2 + 1);
-        gam = __ldg(a.gamma + tx); bet = __ldg(a.beta + tx);
-    }
+    if (tx >= 0 && tx < a.Cin && a.gn_in != nullptr) { gam = __ldg(a.gamma + tx); bet = __ldg(a.beta + tx); }   // constants
 
     if (warp == 0) HX_STAMP(0);
     if (threadIdx.x == 0) {
@@ -175,10 +170,18 @@ __global__ void __launch_bounds__(kThreadsHx, 1) conv_hx_kernel(const HxParams p
         for (int i = 0; i < kMaxSlots; ++i) { mbar_init(&ctl->w_full[i], 1); mbar_init(&ctl->w_empty[i], 1); }
         fence_barrier_init();
     }
-    for (int i = threadIdx.x; i < 4 * 2 * kGroups * 2; i += kThreadsHx) (&ctl->stp[0][0][0])[i] = 0.f;
+    for (int i = threadIdx.x; i < 12 * 2 * kGroups * 2; i += kThreadsHx) (&ctl->stp[0][0][0])[i] = 0.f;
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // everything above is independent of the previous kernel; from here on its outputs (activations, statistics) are read
+    chore_pdl_wait();
+    if (tx >= 0 && tx < a.Cin && a.gn_in != nullptr && (int)blockIdx.x < p.n_items) {
+        // the GroupNorm table inputs of the first item travel while the CTA finishes its set-up
+        const int b0 = ((int)blockIdx.x / nk) / tiles_per_img, g = tx / (a.Cin / kGroups);
+        st_s = __ldcg(a.gn_in + (size_t)b0 * kGroups * 2 + g * 2);
+        st_q = __ldcg(a.gn_in + (size_t)b0 * kGroups * 2 + g * 2 + 1);
     }
     tc_fence_before();
     __syncthreads();
@@ -250,155 +253,8 @@ __global__ void __launch_bounds__(kThreadsHx, 1) conv_hx_kernel(const HxParams p
                 tap = 0; ++kb; ++hc;
             }
         }
-    } else if (warp < kFirstTxWarp) {
-        // ---------------- epilogue ----------------
-        // TMEM gives every lane one pixel row of 32 channels; a warp-wide store in that layout touches 32 different
-        // 128-byte lines.  Each 32 x 32 chunk is therefore transposed through a padded per-warp staging tile: afterwards
-        // lane L holds the channel quad (L & 7) of the rows 4 i + (L >> 3), i = 0..7, and every load / store instruction
-        // of the warp covers 4 full lines.  The per-channel sums for the GroupNorm statistics fall out of that layout
-        // with two shuffles per value.
-        const int quarter = warp & 3;
-        const int et = threadIdx.x - kFirstEpiWarp * 32;    // 0..127
-        const int cq = (lane & 7) * 4, rsub = lane >> 3;    // channel quad inside the chunk, row phase
-        const uint32_t stg = smem_u32(stage) + (uint32_t)quarter * kStageWarpBytes;
-        const uint32_t stg_w = stg + (uint32_t)lane * kStagePitch, stg_r = stg + (uint32_t)rsub * kStagePitch + (uint32_t)(lane & 7) * 16u;
-        float *stp_raw = &ctl->stp[quarter][0][0], *stp_out = &ctl->stp[quarter][1][0];
-        uint32_t ic = 0;
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++ic) {
-            const int ks = item % p.k_splits, tn = item / p.k_splits;        // tn = tile * n_splits + n slice
-            const int tile = tn / p.n_splits, n0 = (tn - tile * p.n_splits) * p.Ns;
-            const int b = tile / tiles_per_img, tt = tile - b * tiles_per_img;
-            const int y0 = (tt / p.tiles_x) * kTileH, x0 = (tt % p.tiles_x) * kTileW;
-            // rows of this lane: tile row r_i = quarter * 32 + 4 i + rsub -> pixel (y0 + r_i / 8, x0 + r_i % 8)
-            int pixv[8];                                     // pixel index inside the tensor, or -1 outside the image
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = quarter * 32 + 4 * i + rsub;
-                const int gy = y0 + (r >> 3), gx = x0 + (r & 7);
-                pixv[i] = (gy < a.H && gx < a.W) ? (b * a.H + gy) * a.W + gx : -1;
-            }
-            const uint32_t abuf = ic & 1u;
-            const uint32_t tacc = tmem_base + abuf * 256u + ((uint32_t)(quarter * 32) << 16);
-            auto load_chunk = [&](int c0, float4 (&x)[8]) {   // TMEM -> staging -> transposed registers
-                uint32_t u[32];
-                tmem_ld32(tacc + (uint32_t)c0, u);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_w + j * 16), "r"(u[4 * j]), "r"(u[4 * j + 1]),
-                                 "r"(u[4 * j + 2]), "r"(u[4 * j + 3]) : "memory");
-                __syncwarp();
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[i].x), "=f"(x[i].y), "=f"(x[i].z), "=f"(x[i].w)
-                                 : "r"(stg_r + i * 4 * kStagePitch) : "memory");
-                __syncwarp();
-            };
-            if (ks != 0) {
-                // K-split follower: park the fp32 partial tile in L2 and signal the leader
-                float *dst = p.part + (((size_t)tn * (p.k_splits - 1) + (ks - 1)) * 128 + quarter * 32 + rsub) * p.Ns + cq;
-                mbar_wait(&ctl->acc_full[abuf], (ic >> 1) & 1u);
-                tc_fence_after();
-                for (int c0 = 0; c0 < p.Ns; c0 += 32) {
-                    float4 x[8];
-                    load_chunk(c0, x);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) __stcg(reinterpret_cast<float4 *>(dst + (size_t)(4 * i) * p.Ns + c0), x[i]);
-                }
-                tc_fence_before();
-                __threadfence();
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(&ctl->acc_empty[abuf]);
-                    asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p.part_cnt + tn) : "memory");
-                }
-                continue;
-            }
-            const bool has_res = a.res != nullptr;
-            float4 rr[8];
-            if (has_res) {                                   // the residual of the first chunk travels while the MMAs run
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    rr[i] = ldcg_pred(a.res + (size_t)(pixv[i] < 0 ? 0 : pixv[i]) * a.ld_res + a.off_res + n0 + cq, pixv[i] >= 0);
-            }
-            mbar_wait(&ctl->acc_full[abuf], (ic >> 1) & 1u);
-            tc_fence_after();
-            if (ic == 0 && warp == kFirstEpiWarp) HX_STAMP(16);
-            if (p.k_splits > 1) {
-                // wait for the 4 epilogue warps of every follower (bounded: a lost arrival must not hang the GPU)
-                if (lane == 0) {
-                    const int want = 4 * (p.k_splits - 1);
-                    int got = 0;
-                    for (int spin = 0; spin < (1 << 24); ++spin) {
-                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(got) : "l"(p.part_cnt + tn) : "memory");
-                        if (got >= want) break;
-                    }
-                }
-                __syncwarp();
-                if (ic == 0 && warp == kFirstEpiWarp) HX_STAMP(19);
-            }
-            const float *part = p.part + (((size_t)tn * (p.k_splits - 1)) * 128 + quarter * 32 + rsub) * p.Ns + cq;
-            for (int c0 = 0; c0 < p.Ns; c0 += 32) {
-                float4 x[8];
-                load_chunk(c0, x);
-                const int c = n0 + c0 + cq;                  // first channel of this lane's quad
-                const bool stamp = ic == 0 && c0 == 0 && warp == kFirstEpiWarp;
-                if (stamp) HX_STAMP(20);
-                for (int k = 1; k < p.k_splits; ++k) {
-                    const float *pk = part + (size_t)(k - 1) * 128 * p.Ns + c0;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float4 pv = __ldcg(reinterpret_cast<const float4 *>(pk + (size_t)(4 * i) * p.Ns));
-                        x[i].x += pv.x; x[i].y += pv.y; x[i].z += pv.z; x[i].w += pv.w;
-                    }
-                }
-                if (a.bias) {
-                    const float4 bb = __ldg(reinterpret_cast<const float4 *>(a.bias + c));
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) { x[i].x += bb.x; x[i].y += bb.y; x[i].z += bb.z; x[i].w += bb.w; }
-                }
-                if (a.raw) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        if (pixv[i] >= 0) *reinterpret_cast<float4 *>(a.raw + (size_t)pixv[i] * a.ld_raw + a.off_raw + c) = x[i];
-                }
-                if (stamp) HX_STAMP(21);
-                if (a.st_raw) stats_quad(a.cpg_raw, x, pixv, a.off_raw + c, stp_raw, lane);
-                if (stamp) HX_STAMP(22);
-                if (has_res) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) { x[i].x += rr[i].x; x[i].y += rr[i].y; x[i].z += rr[i].z; x[i].w += rr[i].w; }
-                    if (c0 + 32 < p.Ns) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            rr[i] = ldcg_pred(a.res + (size_t)(pixv[i] < 0 ? 0 : pixv[i]) * a.ld_res + a.off_res + c + 32, pixv[i] >= 0);
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (pixv[i] >= 0) *reinterpret_cast<float4 *>(a.out + (size_t)pixv[i] * a.ld_out + a.off_out + c) = x[i];
-                if (stamp) HX_STAMP(23);
-                if (a.st_out) stats_quad(a.cpg_out, x, pixv, a.off_out + c, stp_out, lane);
-                if (stamp) HX_STAMP(25);
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (ic == 0 && warp == kFirstEpiWarp) HX_STAMP(17);
-            if (lane == 0) mbar_arrive(&ctl->acc_empty[abuf]);
-            if (a.st_raw || a.st_out) {
-                // flush this item's statistics (they belong to image b): 4 warp slots summed in fixed order, fp64 atomics
-                named_bar(1, 128);
-                const int set = et >> 6, idx = et & 63;
-                double *gst = set ? a.st_out : a.st_raw;
-                double val = 0.0;
-#pragma unroll
-                for (int w = 0; w < 4; ++w) { val += (double)ctl->stp[w][set][idx]; ctl->stp[w][set][idx] = 0.f; }
-                if (gst != nullptr && val != 0.0) atomicAdd(gst + (size_t)b * kGroups * 2 + idx, val);
-                named_bar(1, 128);
-                if (ic == 0 && warp == kFirstEpiWarp) HX_STAMP(18);
-            }
-        }
     } else {
+      if (warp >= kFirstTxWarp) {
         // ---------------- transform: fp32 halo -> relu(groupnorm) -> fp16 hi / lo planes, 128B-swizzled ----------------
         // Thread (q, p0): float4 channel chunk q of the 64-channel k-block, halo pixels p0 + 16 j.  The loads of the NEXT
         // (item, k-block) step are issued while the current one is converted: one step of latency hiding in registers.
@@ -514,6 +370,167 @@ __global__ void __launch_bounds__(kThreadsHx, 1) conv_hx_kernel(const HxParams p
             }
             item = next_item;
         }
+      }
+      {
+        // ---------------- epilogue (warps 2-5: every item; transform warps 6-13: help with the CTA's last item) ----------------
+        // TMEM gives every lane one pixel row of 32 channels; a warp-wide store in that layout touches 32 different
+        // 128-byte lines and the L1 serialises on lines (measured: 8 float4 stores of that shape cost ~1000 cycles; the
+        // 16x256b fragment shape with 8 lines per instruction is no better per byte).  Each 32 x 32 chunk is therefore
+        // transposed through a padded per-warp staging tile: afterwards lane L holds the channel quad (L & 7) of the rows
+        // 4 i + (L >> 3), i = 0..7, and every load / store instruction of the warp covers 4 full lines.  The per-channel
+        // sums for the GroupNorm statistics fall out of that layout with two shuffles per value.
+        // A CTA's last item has no successor to convert halos for, so the 8 transform warps join in (TMEM lanes are bound
+        // to warp % 4: every lane quarter gets three workers, chunks are dealt round-robin; their staging tiles live in the
+        // halo buffers, which are idle once the accumulator is complete).
+        const bool helper = warp >= kFirstTxWarp;
+        const int quarter = warp & 3;
+        const int wslot = helper ? 1 + (warp - kFirstTxWarp) / 4 : 0;           // worker index inside the quarter
+        const int et = threadIdx.x - kFirstEpiWarp * 32;    // 0..127 for the epilogue warps (they flush the statistics)
+        const int cq = (lane & 7) * 4, rsub = lane >> 3;    // channel quad inside the chunk, row phase
+        const uint32_t stg = helper ? smem_u32(halo) + (uint32_t)(warp - kFirstTxWarp) * kStageWarpBytes
+                                    : smem_u32(stage) + (uint32_t)quarter * kStageWarpBytes;
+        const int last_ic = (p.n_items - 1 - (int)blockIdx.x) / (int)gridDim.x;      // index of this CTA's last item
+        const uint32_t stg_w = stg + (uint32_t)lane * kStagePitch, stg_r = stg + (uint32_t)rsub * kStagePitch + (uint32_t)(lane & 7) * 16u;
+        float *stp_raw = &ctl->stp[quarter * 3 + wslot][0][0], *stp_out = &ctl->stp[quarter * 3 + wslot][1][0];
+        const int n_chunks = p.Ns / 32;
+        uint32_t ic = helper ? (uint32_t)last_ic : 0u;
+        for (int item = blockIdx.x + (int)ic * (int)gridDim.x; item < p.n_items; item += gridDim.x, ++ic) {
+            const bool last = (int)ic == last_ic;
+            const int workers = last ? 3 : 1;
+            const int ks = item % p.k_splits, tn = item / p.k_splits;        // tn = tile * n_splits + n slice
+            const int tile = tn / p.n_splits, n0 = (tn - tile * p.n_splits) * p.Ns;
+            const int b = tile / tiles_per_img, tt = tile - b * tiles_per_img;
+            const int y0 = (tt / p.tiles_x) * kTileH, x0 = (tt % p.tiles_x) * kTileW;
+            // rows of this lane: tile row r_i = quarter * 32 + 4 i + rsub -> pixel (y0 + r_i / 8, x0 + r_i % 8)
+            int pixv[8];                                     // pixel index inside the tensor, or -1 outside the image
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = quarter * 32 + 4 * i + rsub;
+                const int gy = y0 + (r >> 3), gx = x0 + (r & 7);
+                pixv[i] = (gy < a.H && gx < a.W) ? (b * a.H + gy) * a.W + gx : -1;
+            }
+            const uint32_t abuf = ic & 1u;
+            const uint32_t tacc = tmem_base + abuf * 256u + ((uint32_t)(quarter * 32) << 16);
+            auto load_chunk = [&](int c0, float4 (&x)[8]) {   // TMEM -> staging -> transposed registers
+                uint32_t u[32];
+                tmem_ld32(tacc + (uint32_t)c0, u);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg_w + j * 16), "r"(u[4 * j]), "r"(u[4 * j + 1]),
+                                 "r"(u[4 * j + 2]), "r"(u[4 * j + 3]) : "memory");
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[i].x), "=f"(x[i].y), "=f"(x[i].z), "=f"(x[i].w)
+                                 : "r"(stg_r + i * 4 * kStagePitch) : "memory");
+                __syncwarp();
+            };
+            const bool res_on = a.res != nullptr;
+            float4 rr[8];
+            auto load_res = [&](int c) {                    // c = absolute first channel of this lane's quad
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    rr[i] = ldcg_pred(a.res + (size_t)(pixv[i] < 0 ? 0 : pixv[i]) * a.ld_res + a.off_res + c, pixv[i] >= 0);
+            };
+            // K split: chunk ci is finished by part ci % k_splits; without a split this part owns every chunk
+            // ... and the chunks a part finishes are dealt to its `workers` warps of this lane quarter
+            const int c_first = (ks + wslot * p.k_splits) * 32, c_step = 32 * p.k_splits * workers;
+            if (res_on && c_first < p.Ns) load_res(n0 + c_first + cq);     // travels while the MMAs run
+            mbar_wait(&ctl->acc_full[abuf], (ic >> 1) & 1u);
+            tc_fence_after();
+            if (ic == 0 && warp == kFirstEpiWarp) HX_STAMP(16);
+            const size_t prow = (size_t)(quarter * 32 + rsub) * p.Ns + cq;   // this lane's first row / quad inside a partial tile
+            if (p.k_splits > 1) {
+                // park the chunks other parts own in the L2-resident scratch, signal, wait for everybody
+                float *mine = p.part + (size_t)(tn * p.k_splits + ks) * 128 * p.Ns + prow;
+                int parked = 0;
+                for (int ci = 0; ci < n_chunks; ++ci) {
+                    if (ci % p.k_splits == ks) continue;
+                    if ((parked++) % workers != wslot) continue;
+                    float4 x[8];
+                    load_chunk(ci * 32, x);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) __stcg(reinterpret_cast<float4 *>(mine + (size_t)(4 * i) * p.Ns + ci * 32), x[i]);
+                }
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p.part_cnt + tn) : "memory");
+                    if (c_first < p.Ns) {                   // bounded wait: a lost arrival must not hang the GPU
+                        const int want = 4 * workers * p.k_splits;
+                        int got = 0;
+                        for (int spin = 0; spin < (1 << 24); ++spin) {
+                            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(got) : "l"(p.part_cnt + tn) : "memory");
+                            if (got >= want) break;
+                        }
+                    }
+                }
+                __syncwarp();
+                if (ic == 0 && warp == kFirstEpiWarp) HX_STAMP(19);
+            }
+            for (int c0 = c_first; c0 < p.Ns; c0 += c_step) {
+                float4 x[8];
+                load_chunk(c0, x);
+                const int c = n0 + c0 + cq;                  // absolute first channel of this lane's quad
+                const bool stamp = ic == 0 && c0 == c_first && warp == kFirstEpiWarp;
+                if (stamp) HX_STAMP(20);
+                for (int k2 = 0; k2 < p.k_splits; ++k2) {
+                    if (k2 == ks) continue;
+                    const float *pk = p.part + (size_t)(tn * p.k_splits + k2) * 128 * p.Ns + prow + c0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 pv = __ldcg(reinterpret_cast<const float4 *>(pk + (size_t)(4 * i) * p.Ns));
+                        x[i].x += pv.x; x[i].y += pv.y; x[i].z += pv.z; x[i].w += pv.w;
+                    }
+                }
+                if (a.bias) {
+                    const float4 bb = __ldg(reinterpret_cast<const float4 *>(a.bias + c));
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { x[i].x += bb.x; x[i].y += bb.y; x[i].z += bb.z; x[i].w += bb.w; }
+                }
+                if (a.raw) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (pixv[i] >= 0) *reinterpret_cast<float4 *>(a.raw + (size_t)pixv[i] * a.ld_raw + a.off_raw + c) = x[i];
+                }
+                if (stamp) HX_STAMP(21);
+                if (a.st_raw) stats_quad(a.cpg_raw, x, pixv, a.off_raw + c, stp_raw, lane);
+                if (stamp) HX_STAMP(22);
+                if (res_on) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { x[i].x += rr[i].x; x[i].y += rr[i].y; x[i].z += rr[i].z; x[i].w += rr[i].w; }
+                    if (c0 + c_step < p.Ns) load_res(c + c_step);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (pixv[i] >= 0) *reinterpret_cast<float4 *>(a.out + (size_t)pixv[i] * a.ld_out + a.off_out + c) = x[i];
+                if (stamp) HX_STAMP(23);
+                if (a.st_out) stats_quad(a.cpg_out, x, pixv, a.off_out + c, stp_out, lane);
+                if (stamp) HX_STAMP(25);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (ic == 0 && warp == kFirstEpiWarp) HX_STAMP(17);
+            if (lane == 0 && !helper) mbar_arrive(&ctl->acc_empty[abuf]);
+            if (a.st_raw || a.st_out) {
+                // flush this item's statistics (they belong to image b): the worker slots summed in fixed order, fp64 atomics
+                // (two barrier ids: the helpers can reach the last item's barrier while the epilogue warps are still inside
+                // the previous item's, the accumulators being double buffered)
+                if (last) named_bar(3, 128 * 3); else named_bar(1, 128);
+                if (!helper) {
+                    const int set = et >> 6, idx = et & 63;
+                    double *gst = set ? a.st_out : a.st_raw;
+                    double val = 0.0;
+#pragma unroll
+                    for (int w = 0; w < 12; ++w) { val += (double)ctl->stp[w][set][idx]; ctl->stp[w][set][idx] = 0.f; }
+                    if (gst != nullptr && val != 0.0) atomicAdd(gst + (size_t)b * kGroups * 2 + idx, val);
+                }
+                if (!last) named_bar(1, 128);            // the slots are clear before the next item writes them
+                if (ic == 0 && warp == kFirstEpiWarp) HX_STAMP(18);
+            }
+        }
+      }
     }
     tc_fence_before();
     __syncthreads();
@@ -597,7 +614,7 @@ int conv_hx_plan(const chore_handle *h, const ConvHxArgs &a, ConvHxPlan *pl) {
     int ns = 1;
     while (tiles * ks * ns * 2 <= h->sm_count && a.N / (ns * 2) >= 32) ns *= 2;
     pl->tiles = tiles; pl->k_splits = ks; pl->n_splits = ns;
-    pl->part_floats = ks > 1 ? (size_t)tiles * ns * (ks - 1) * 128 * (a.N / ns) : 0;
+    pl->part_floats = ks > 1 ? (size_t)tiles * ns * ks * 128 * (a.N / ns) : 0;
     pl->counters = ks > 1 ? tiles * ns : 0;
     return CHORE_OK;
 }
@@ -631,7 +648,7 @@ int conv_hx_launch(chore_handle *h, const ConvHxArgs &a, const ConvHxPlan &pl, f
     const size_t smem = fixed + (size_t)p.n_slots * p.w_slot;
     const int grid = p.n_items < h->sm_count ? p.n_items : h->sm_count;
     p.trace = (g_hx_trace != nullptr && g_hx_trace_idx < 256) ? g_hx_trace + 32 * (g_hx_trace_idx++) : nullptr;
-    if (a.KS == 3) CHORE_LAUNCH(conv_hx_kernel<3>, grid, kThreadsHx, smem, st, p);
-    else CHORE_LAUNCH(conv_hx_kernel<1>, grid, kThreadsHx, smem, st, p);
+    if (a.KS == 3) CHORE_LAUNCH_PDL(conv_hx_kernel<3>, dim3(grid), dim3(kThreadsHx), smem, st, p);
+    else CHORE_LAUNCH_PDL(conv_hx_kernel<1>, dim3(grid), dim3(kThreadsHx), smem, st, p);
     return CHORE_OK;
 }

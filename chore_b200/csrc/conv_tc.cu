@@ -318,19 +318,11 @@ int conv_tc_launch(const ConvTcArgs &a, cudaStream_t st) {
     const size_t stage = 32768 + 2 * (size_t)a.Cout * 128;
     if (a.Cout <= 128) {
         const size_t smem = 1024 + 3 * stage + 128;
-        static bool configured = false;
-        if (!configured) {
-            CHORE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + 3 * 65536 + 128));
-            configured = true;
-        }
+        CHORE_ONCE_PER_DEVICE(cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + 3 * 65536 + 128));
         CHORE_LAUNCH(conv_tc_kernel<3>, grid, kThreadsConv, smem, st, map_hi, map_lo, p);
     } else {
         const size_t smem = 1024 + 2 * stage + 128;
-        static bool configured = false;
-        if (!configured) {
-            CHORE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + 2 * 98304 + 128));
-            configured = true;
-        }
+        CHORE_ONCE_PER_DEVICE(cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + 2 * 98304 + 128));
         CHORE_LAUNCH(conv_tc_kernel<2>, grid, kThreadsConv, smem, st, map_hi, map_lo, p);
     }
     return CHORE_OK;

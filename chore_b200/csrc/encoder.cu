@@ -466,11 +466,8 @@ double *gn_stats(Ctx &c, const float *in, int ld, int off, int C, int H, int W) 
 template <int KS, int COT>
 void launch_conv(Ctx &c, const ConvArgs &a) {
     using S = ConvSmem<KS, COT>;
-    static bool configured = false;
-    if (!configured && !c.dry) {
-        cudaFuncSetAttribute(conv_kernel<KS, COT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::bytes);
-        configured = true;
-    }
+    if (!c.dry && c.rc == 0)
+        c.rc = []() -> int { CHORE_ONCE_PER_DEVICE(cudaFuncSetAttribute(conv_kernel<KS, COT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::bytes)); return (int)CHORE_OK; }();
     const int tiles = ((a.W + kTW - 1) / kTW) * ((a.H + kTH - 1) / kTH);
     dim3 grid(tiles, a.Cout / COT, a.B);
     auto kern = conv_kernel<KS, COT>;
@@ -592,11 +589,8 @@ void run_graph(Ctx &c, const float *images, int H, int W, float *feat, float *sk
     {
         dim3 grid((W2 + kStemTile - 1) / kStemTile, (H2 + kStemTile - 1) / kStemTile, c.B);
         const size_t smem = (size_t)(kStemPatchFloats + CHORE_IN_CH * 49 * 64) * sizeof(float);
-        static bool configured = false;
-        if (!configured && !c.dry) {
-            cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            configured = true;
-        }
+        if (!c.dry && c.rc == 0)
+            c.rc = [smem]() -> int { CHORE_ONCE_PER_DEVICE(cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); return (int)CHORE_OK; }();
         const ConvW &w = cw(c, p + ".conv1");
         ENC_LAUNCH(c, stem_conv_kernel, grid, 256, smem, images, H, W, w.w, w.bias, s0.p);
     }

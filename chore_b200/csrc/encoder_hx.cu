@@ -60,6 +60,8 @@ __device__ __forceinline__ void gn_affine_hx(const double *__restrict__ sums, in
 __global__ void __launch_bounds__(256) gn_apply_stats_kernel(const float *__restrict__ in, float *__restrict__ out, int C, int HW,
                                                              const double *__restrict__ sums, const float *__restrict__ gamma,
                                                              const float *__restrict__ beta, double *__restrict__ st_out) {
+    chore_pdl_launch_dependents();
+    chore_pdl_wait();
     __shared__ float acc[kGroups * 2];
     const int b = blockIdx.y, tid = threadIdx.x, c4n = C / 4, cpg = C / kGroups;
     if (tid < kGroups * 2) acc[tid] = 0.f;
@@ -86,6 +88,8 @@ __global__ void __launch_bounds__(256) gn_apply_stats_kernel(const float *__rest
 // avg-pool 2x2 stride 2 (F.avg_pool2d, model/HGFilters.py:32,152) + statistics of the result
 __global__ void __launch_bounds__(256) avgpool_stats_kernel(const float *__restrict__ in, float *__restrict__ out, int H, int W, int C,
                                                             double *__restrict__ st_out) {
+    chore_pdl_launch_dependents();
+    chore_pdl_wait();
     __shared__ float acc[kGroups * 2];
     const int b = blockIdx.y, tid = threadIdx.x, c4n = C / 4, cpg = C / kGroups, OW = W / 2, OH = H / 2;
     if (tid < kGroups * 2) acc[tid] = 0.f;
@@ -124,6 +128,8 @@ __device__ __forceinline__ void cubic_coeffs_hx(float t, float (&c)[4]) {
 
 __global__ void __launch_bounds__(256) upadd_stats_kernel(const float *__restrict__ low, float *__restrict__ up, int IH, int IW, int C,
                                                           double *__restrict__ st_out) {
+    chore_pdl_launch_dependents();
+    chore_pdl_wait();
     __shared__ float acc[kGroups * 2];
     const int b = blockIdx.y, tid = threadIdx.x, c4n = C / 4, cpg = C / kGroups, OW = IW * 2, OH = IH * 2;
     if (tid < kGroups * 2) acc[tid] = 0.f;
@@ -174,6 +180,7 @@ constexpr int kStemPatchFloats = (CHORE_IN_CH * kStemPatch * (kStemPatch + 1) + 
 
 __global__ void __launch_bounds__(256) stem_hx_kernel(const float *__restrict__ img, int H, int W, const float *__restrict__ w /*[5*49][64]*/,
                                                       const float *__restrict__ bias, float *__restrict__ out, double *__restrict__ st_out) {
+    chore_pdl_launch_dependents();
     extern __shared__ __align__(16) float smem[];
     __shared__ double acc[kGroups * 2];
     float *patch = smem;                                           // [5][37][38]
@@ -197,6 +204,7 @@ __global__ void __launch_bounds__(256) stem_hx_kernel(const float *__restrict__ 
     const int ty = tid / kStemTile, tx = tid % kStemTile;
     const int oy = oy0 + ty, ox = ox0 + tx;
     const bool valid = oy < OH && ox < OW;
+    chore_pdl_wait();                  // `out` / the statistics slot may still be in use by the previous kernel of the stream
 #pragma unroll 1
     for (int pass = 0; pass < 4; ++pass) {
         float a[16];
@@ -283,9 +291,8 @@ struct CtxH {
 #define HX_LAUNCH(ctx, kernel, grid, block, smem, ...)                                       \
     do {                                                                                     \
         if (!(ctx).dry && (ctx).rc == 0) {                                                   \
-            kernel<<<(grid), (block), (smem), (ctx).st>>>(__VA_ARGS__);                      \
+            cudaError_t e_ = chore_launch_pdl(kernel, dim3(grid), dim3(block), (smem), (ctx).st, __VA_ARGS__); \
             g_launch_count.fetch_add(1, std::memory_order_relaxed);                          \
-            cudaError_t e_ = cudaGetLastError();                                             \
             if (e_ != cudaSuccess) {                                                         \
                 chore_set_error("%s:%d: launch of %s -> %s", __FILE__, __LINE__, #kernel, cudaGetErrorString(e_)); \
                 (ctx).rc = CHORE_ERR_CUDA;                                                   \

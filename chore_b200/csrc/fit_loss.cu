@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(128) fit_pose_prior_kernel(const float *__rest
             g[66 + tid] += 2.f * ch * a;
         }
     }
+    __syncthreads();   // g[66..71] is touched by the hand-prior threads 0..5 above and by the pinit threads 63..68 below
     if (pose_init != nullptr && tid < 69) {
         const float df = p[3 + tid] - pose_init[(size_t)b * 69 + tid];
         l += cp * df * df;
@@ -262,15 +263,18 @@ struct AdamArgs {
 };
 // torch.optim.Adam(betas=(b1,b2), eps, weight_decay=0, amsgrad=False), single block so that the device-side step
 // counter (needed under CUDA-graph replay: kernel arguments are frozen) is read by every thread before it is bumped.
-__global__ void __launch_bounds__(256) adam_step_kernel(const AdamArgs a, float lr, float b1, float b2, float eps, int *__restrict__ step) {
+__global__ void __launch_bounds__(256) adam_step_kernel(const AdamArgs a, float lr, float b1, float b2, float eps, int *__restrict__ step,
+                                                        const float *__restrict__ gscale, float *__restrict__ loss_inout) {
     const int t = step[0] + 1;
+    const float gs = gscale != nullptr ? gscale[0] : 1.f;
     const float bc1 = 1.f - powf(b1, (float)t), bc2 = 1.f - powf(b2, (float)t);
     const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
     for (int k = 0; k < a.n; ++k) {
         const chore_adam_entry e = a.e[k];
         for (int i = threadIdx.x; i < e.rows * e.cols; i += blockDim.x) {
             const int r = i / e.cols, c = i - r * e.cols;
-            const float g = e.grad[(size_t)r * e.grad_ld + c];
+            float g = gs * e.grad[(size_t)r * e.grad_ld + c];
+            if (e.grad_acc != nullptr) { g += e.grad_acc[i]; e.grad_acc[i] = g; }   // sum since the last zero_grad()
             const float m = b1 * e.exp_avg[i] + (1.f - b1) * g;
             const float v = b2 * e.exp_avg_sq[i] + (1.f - b2) * g * g;
             e.exp_avg[i] = m; e.exp_avg_sq[i] = v;
@@ -278,7 +282,10 @@ __global__ void __launch_bounds__(256) adam_step_kernel(const AdamArgs a, float 
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) step[0] = t;
+    if (threadIdx.x == 0) {
+        step[0] = t;
+        if (loss_inout != nullptr) loss_inout[0] *= gs;
+    }
 }
 
 }   // namespace
@@ -348,7 +355,7 @@ extern "C" int chore_add_rowvec(chore_handle *h, float *x, const float *v, int B
 }
 
 extern "C" int chore_adam_step(chore_handle *h, const chore_adam_entry *entries, int n, float lr, float beta1, float beta2, float eps,
-                               int32_t *step, void *stream) {
+                               int32_t *step, const float *gscale, float *loss_inout, void *stream) {
     CHORE_CHECK(h && entries && step && n > 0 && n <= CHORE_ADAM_MAX_ENTRIES, "bad arguments (1..%d entries)", CHORE_ADAM_MAX_ENTRIES);
     AdamArgs a{};
     a.n = n;
@@ -357,7 +364,7 @@ extern "C" int chore_adam_step(chore_handle *h, const chore_adam_entry *entries,
                     entries[i].cols > 0 && entries[i].grad_ld >= entries[i].cols, "entry %d is malformed", i);
         a.e[i] = entries[i];
     }
-    CHORE_LAUNCH(adam_step_kernel, 1, 256, 0, static_cast<cudaStream_t>(stream), a, lr, beta1, beta2, eps, step);
+    CHORE_LAUNCH(adam_step_kernel, 1, 256, 0, static_cast<cudaStream_t>(stream), a, lr, beta1, beta2, eps, step, gscale, loss_inout);
     return CHORE_OK;
 }
 

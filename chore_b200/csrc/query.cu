@@ -529,11 +529,7 @@ void fill_weights(QueryParams &q, const MlpWeights &m) {
 template <int P>
 int launch_fwd(const QueryParams &q, int grid_y, cudaStream_t st) {
     constexpr size_t smem = fwd_smem_floats<P>() * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-        CHORE_CUDA(cudaFuncSetAttribute(query_fwd_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    CHORE_ONCE_PER_DEVICE(cudaFuncSetAttribute(query_fwd_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long tiles = (q.n_count + P - 1) / P;
     CHORE_CHECK(tiles < (1ll << 31), "too many points per launch");
     dim3 grid((unsigned)tiles, (unsigned)grid_y);
@@ -734,11 +730,7 @@ extern "C" int chore_query_bwd_ws(chore_handle *h, const float *feat, const floa
     q.g_points = g_points;
     fill_weights(q, h->mlp);
     constexpr size_t smem = bwd_smem_bytes<P>();
-    static bool configured = false;
-    if (!configured) {
-        CHORE_CUDA(cudaFuncSetAttribute(query_bwd_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    CHORE_ONCE_PER_DEVICE(cudaFuncSetAttribute(query_bwd_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((N + P - 1) / P), (unsigned)B);
     CHORE_LAUNCH(query_bwd_kernel<P>, grid, NT, smem, static_cast<cudaStream_t>(stream), q);
     return CHORE_OK;

@@ -938,11 +938,7 @@ int query_bwd_tc_launch(chore_handle *h, const float *feat, const float *skip, i
     }
     q.gx_slot_stride = (long long)B * N * kGXLd;
     q.wstream_bwd = m.wstream_bwd;
-    static bool configured = false;
-    if (!configured) {
-        CHORE_CUDA(cudaFuncSetAttribute(query_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemBytes));
-        configured = true;
-    }
+    CHORE_ONCE_PER_DEVICE(cudaFuncSetAttribute(query_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmemBytes));
     if (nslots > 1) {
         q.bwd_nslots = nslots; q.bwd_accumulate = 0;
         for (int i = 0; i < nslots; ++i) { q.bwd_heads[i] = heads[i]; q.g_heads[i] = g_heads[heads[i]]; }
@@ -982,11 +978,7 @@ int query_tc_launch(chore_handle *h, const float *feat, const float *skip, int f
     q.wstream = m.wstream; q.b1 = m.b1; q.b2 = m.b2; q.b3 = m.b3; q.w4 = m.w4; q.b4 = m.b4;
     q.tiles_per_b = (n_count + kTileM - 1) / kTileM;
     q.total_tiles = q.tiles_per_b * (grid_mode ? 1 : B);
-    static bool configured = false;
-    if (!configured) {
-        CHORE_CUDA(cudaFuncSetAttribute(query_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        configured = true;
-    }
+    CHORE_ONCE_PER_DEVICE(cudaFuncSetAttribute(query_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     const long long grid = q.total_tiles < h->sm_count ? q.total_tiles : h->sm_count;
     static const bool trace = getenv("CHORE_B200_TC_TRACE") != nullptr;
     unsigned long long *dbg = nullptr;

@@ -459,11 +459,7 @@ int query_tc2_launch(chore_handle *h, const float *feat, const float *skip, int 
     q.wstream = m.wstream; q.b1 = m.b1; q.b2 = m.b2; q.b3 = m.b3; q.w4 = m.w4; q.b4 = m.b4;
     q.tiles_per_b = (n_count + kTileM - 1) / kTileM;
     q.total_tiles = q.tiles_per_b * (grid_mode ? 1 : B);
-    static bool configured = false;
-    if (!configured) {
-        CHORE_CUDA(cudaFuncSetAttribute(query_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes2));
-        configured = true;
-    }
+    CHORE_ONCE_PER_DEVICE(cudaFuncSetAttribute(query_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes2));
     const long long pairs = (q.total_tiles + 1) / 2;
     const long long clusters = pairs < h->sm_count / 2 ? pairs : h->sm_count / 2;
     cudaLaunchConfig_t cfg{};

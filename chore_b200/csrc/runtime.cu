@@ -3,9 +3,18 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 std::atomic<uint64_t> g_launch_count{0};
+
+bool chore_pdl_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("CHORE_B200_PDL");      // opt-in: measured no gain inside a CUDA graph (2.78 vs 2.69 ms per image)
+        return e != nullptr && e[0] == '1';
+    }();
+    return on;
+}
 static thread_local char g_err[512] = "";
 
 void chore_set_error(const char *fmt, ...) {
@@ -35,7 +44,7 @@ int chore_ws2_reserve(chore_handle *h, size_t bytes) { return reserve(&h->ws2, &
 int chore_lbs_ws_reserve(chore_handle *h, size_t bytes) { return reserve(&h->lbs_ws, &h->lbs_ws_bytes, bytes); }
 
 extern "C" const char *chore_last_error(void) { return g_err; }
-extern "C" int chore_abi_version(void) { return 1; }
+extern "C" int chore_abi_version(void) { return 2; }
 extern "C" uint64_t chore_launch_count(void) { return g_launch_count.load(); }
 
 extern "C" int chore_create(int device, chore_handle **out) {

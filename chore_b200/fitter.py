@@ -116,8 +116,13 @@ class GraphedStep:
     `torch.optim.Adam(..., capturable=True)` and device-side RNG) and return the loss tensor(s); the
     returned tensors are refreshed in place by every `__call__`."""
 
-    def __init__(self, step_fn: Callable, warmup: int = 3):
+    def __init__(self, step_fn: Callable, warmup: int = 3, snapshot: Optional[Callable] = None,
+                 restore: Optional[Callable] = None):
+        """snapshot() / restore(state): the warm-up runs `step_fn` for real (lazy allocations must happen outside the
+        capture); when the step mutates optimiser state, pass these so the warm-up steps are undone and a fixed
+        schedule of N replays applies exactly N updates."""
         self.step_fn = step_fn
+        state = snapshot() if snapshot is not None else None
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -125,6 +130,9 @@ class GraphedStep:
                 step_fn()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        if restore is not None:
+            restore(state)
+            torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         inner = None
         try:
@@ -169,6 +177,10 @@ class ReconFitterBase:
         self.priors = priors
         self.net_in_size = net_in_size
         self.crop_size = float(crop_size)
+        if self.crop_size != 1200.0:
+            # the query kernels project with KinectColorCamera(loadSize = 1200) (csrc/query_tc_shared.cuh); a different
+            # crop here would make the keypoint term and the field query disagree silently
+            raise ValueError(f"chore_b200 is built for loadSize / crop_size 1200, got {crop_size}")
         self.strict = strict
         # KinectColorCamera pixel intrinsics (model/camera.py:26-40)
         self.fx_px, self.fy_px = 979.7844 / 2048. * 2048, 979.840 / 2048. * 2048
@@ -424,9 +436,14 @@ class FusedAdam:
     8 small tensors (chore_adam_step); the step counter lives on the device, so a captured step replays correctly.
     `grads[i]` is the tensor the gradient of params[i] is read from at step() time: a (rows, cols) view that may be a
     column slice of a wider, persistent buffer (its storage must not move between steps -- true inside a CUDA graph
-    and for buffers the caller keeps)."""
+    and for buffers the caller keeps).
 
-    def __init__(self, params, lr=0.006, betas=(0.9, 0.999), eps=1e-8, handle=None):
+    accumulate=True keeps one accumulator per parameter and gives the update the SUM of the gradients passed to step()
+    since the last zero_grad() -- what `.grad` holds in the reference loops, which call optimizer.zero_grad() once per
+    outer iteration and loss.backward() in each of the 10 inner steps (recon/recon_fit_behave.py:135-152,244-273).
+    `gscale` (device scalar, optional) multiplies every gradient: the 1 / (1 + decay) of get_loss_weights."""
+
+    def __init__(self, params, lr=0.006, betas=(0.9, 0.999), eps=1e-8, handle=None, accumulate: bool = False):
         self.params = [p for p in params]
         assert 0 < len(self.params) <= 8
         self.lr, self.betas, self.eps = float(lr), betas, float(eps)
@@ -434,17 +451,36 @@ class FusedAdam:
         self.handle = handle or _lib.get_handle(dev)
         self.exp_avg = [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in self.params]
         self.exp_avg_sq = [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in self.params]
+        # `.grad` of every parameter IS its accumulator (as in torch, where backward() adds into .grad)
+        self.accumulate = accumulate
+        self.grad_acc = [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in self.params]
+        for p, a in zip(self.params, self.grad_acc):
+            p.grad = a
         self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
 
-    def step(self, grads) -> None:
+    def zero_grad(self) -> None:
+        torch._foreach_zero_(self.grad_acc)
+
+    def state(self):
+        return [t.detach().clone() for t in (*self.params, *self.exp_avg, *self.exp_avg_sq, *self.grad_acc, self.step_count)]
+
+    def load_state(self, state) -> None:
+        with torch.no_grad():
+            for t, sv in zip((*self.params, *self.exp_avg, *self.exp_avg_sq, *self.grad_acc, self.step_count), state):
+                t.copy_(sv)
+
+    def step(self, grads, gscale: Optional[torch.Tensor] = None, loss: Optional[torch.Tensor] = None) -> None:
+        if not self.accumulate:
+            self.zero_grad()
         ent = (_lib.AdamEntry * len(self.params))()
-        for e, p, g, m, v in zip(ent, self.params, grads, self.exp_avg, self.exp_avg_sq):
+        for i, (e, p, g, m, v) in enumerate(zip(ent, self.params, grads, self.exp_avg, self.exp_avg_sq)):
             p2 = p.detach().view(p.shape[0], -1) if p.dim() > 1 else p.detach().view(1, -1)
             g2 = g.view(g.shape[0], -1) if g.dim() > 1 else g.view(1, -1)
             assert p2.is_contiguous() and g2.stride(-1) == 1 and g2.shape == p2.shape and g2.dtype == torch.float32
             e.param, e.grad, e.exp_avg, e.exp_avg_sq = p2.data_ptr(), g2.data_ptr(), m.data_ptr(), v.data_ptr()
+            e.grad_acc = self.grad_acc[i].data_ptr()
             e.rows, e.cols, e.grad_ld = p2.shape[0], p2.shape[1], (g2.stride(0) if g2.shape[0] > 1 else p2.shape[1])
-        self.handle.adam_step(ent, len(self.params), self.lr, self.betas[0], self.betas[1], self.eps, self.step_count)
+        self.handle.adam_step(ent, len(self.params), self.lr, self.betas[0], self.betas[1], self.eps, self.step_count, gscale, loss)
 
 
 class FusedFitSteps:
@@ -464,22 +500,35 @@ class FusedFitSteps:
          "pose": 1e-5, "hand": 1e-5, "smplz": 30 ** 2, "j2d": 0.3 ** 2}
 
     def __init__(self, net, smpl, data_dict, obj_R, obj_t, obj_s, lr_smpl=0.006, lr_obj=0.006, obj_scale=1.0, decay=1.0,
-                 fitter: Optional["ReconFitterBase"] = None, phase: str = "smpl all pose"):
+                 fitter: Optional["ReconFitterBase"] = None, phase: str = "smpl all pose", accumulate: bool = True):
         """fitter: supplies the priors / camera constants for the pose-prior, hand-prior, smplz and (phase 'kpts')
         2-D keypoint terms of forward_smpl; without it only the field terms (+ pinit) are used.  The landmark terms
-        need regressors on `smpl`."""
+        need regressors on `smpl`.
+
+        Reference semantics of the loop around the step (recon/recon_fit_behave.py:90-163,224-291):
+          * accumulate=True: gradients add up between zero_grad() calls (the reference zeroes once per OUTER iteration,
+            so inner step i sees the sum of the gradients of inner steps 0..i); call zero_grad() where it does.
+          * set_decay(decay): every loss weight is divided by (1 + decay) (1 in the early phases, it / 3 in 'kpts');
+            the factor lives in a device scalar, so captured graphs follow the schedule.
+          * set_phase('global' | 'smpl all pose' | 'kpts'): 'global' optimises top_betas + trans with lr 0.02, the
+            switch to 'smpl all pose' creates a fresh Adam (lr 0.006) like the reference, 'kpts' keeps it and adds j2d."""
         self.net, self.smpl, self.data = net, smpl, data_dict
-        self.fitter, self.phase = fitter, phase
+        self.fitter = fitter
         self.R, self.t, self.s = obj_R, obj_t, obj_s
-        self.obj_scale, self.decay = obj_scale, decay
-        self.smpl_params = [smpl.trans, smpl.global_pose, smpl.body_pose, smpl.top_betas, smpl.other_betas]
+        self.obj_scale = obj_scale
+        self.accumulate = accumulate
         self.h_net = net.handle
         self.h_lbs = smpl.smpl.handle
         self.h_aux = _lib.get_handle(obj_t.device)
-        self.opt_smpl = FusedAdam(self.smpl_params, lr_smpl, handle=self.h_aux)
-        self.opt_obj = FusedAdam([obj_t, obj_R, obj_s], lr_obj, handle=self.h_aux)
-        self.cc = data_dict["query_dict"]["crop_center"].detach().float().contiguous()
         dev = obj_t.device
+        self.kdev = torch.ones(1, device=dev)             # 1 / (1 + decay), read by the Adam kernel
+        self.lr_smpl = lr_smpl
+        self.phase = None
+        self.opt_smpl = None
+        self.set_phase(phase)
+        self.set_decay(decay)
+        self.opt_obj = FusedAdam([obj_t, obj_R, obj_s], lr_obj, handle=self.h_aux, accumulate=accumulate)
+        self.cc = data_dict["query_dict"]["crop_center"].detach().float().contiguous()
         nmax = max(smpl.offsets.shape[1], data_dict["objects"].shape[1]) if "objects" in data_dict else smpl.offsets.shape[1]
         self.ws = self.h_aux.fit_workspace(obj_t.shape[0], nmax, dev)
         self.loss_smpl = torch.zeros(1, device=dev)
@@ -492,6 +541,29 @@ class FusedFitSteps:
                                     (bp.mean.reshape(-1), bp.prec, hp.mean.reshape(-1), hp.lhand_prec[0], hp.rhand_prec[0]))
         self.pose_init = data_dict["pose_init"].detach().float().contiguous() if "pose_init" in data_dict else None
 
+    # ---- schedule hooks (the Python around the step in optimize_smpl / optimize_smpl_object) -------------------
+    def set_phase(self, phase: str) -> None:
+        sm = self.smpl
+        assert phase in ("global", "smpl all pose", "kpts"), phase
+        if phase == "global":
+            names, lr = ("top_betas", "trans"), 0.02                     # recon_fit_behave.py:233
+        else:
+            names, lr = ("trans", "global_pose", "body_pose", "top_betas", "other_betas"), self.lr_smpl   # :250-253
+        fresh = self.opt_smpl is None or names != self.smpl_names        # 'kpts' keeps the optimiser of 'smpl all pose'
+        self.phase, self.smpl_names = phase, names
+        if fresh:
+            self.smpl_params = [getattr(sm, n) for n in names]
+            self.opt_smpl = FusedAdam(self.smpl_params, lr, handle=self.h_aux, accumulate=self.accumulate)
+
+    def set_decay(self, decay: float) -> None:
+        self.decay = float(decay)
+        self.kdev.fill_(1.0 / (1.0 + self.decay))
+
+    def zero_grad(self) -> None:
+        """optimizer.zero_grad() of the reference loops: once per outer iteration."""
+        self.opt_smpl.zero_grad()
+        self.opt_obj.zero_grad()
+
     @torch.no_grad()
     def smpl_step(self):
         sm, d = self.smpl, self.data
@@ -503,7 +575,7 @@ class FusedFitSteps:
         verts, _, _, _ = self.h_lbs.lbs_fwd(pose, betas, trans, off, want_posed=False)
         (df, _, parts, _), _ = self.h_net.query_fwd(feat, skip, verts, self.cc, _lib.HEAD_DF | _lib.HEAD_PARTS)
         B, _, N = df.shape
-        k = 1.0 / (1.0 + self.decay)
+        k = 1.0          # the 1 / (1 + decay) factor is applied to the summed gradient and the loss by the Adam kernel (kdev)
         # L = w_dfh * mean(min(df_h, 0.1)) + w_part * mean_b sum_n CE(parts, labels)
         g_df, g_parts = self.h_aux.fit_smpl_field_grads(df, parts, d["part_labels"], self.W["df_h"] * k / (B * N), self.W["part"] * k / B,
                                                         loss, self.ws)
@@ -525,10 +597,11 @@ class FusedFitSteps:
             # 5^2 * mean_b sum (pose[3:72] - pose_init)^2 (recon_fit_behave.py:317-319)
             self.h_aux.fit_pose_prior_grads(pose, self.pose_init, self.priors_dev, self.W["pose"] * k / B, self.W["hand"] * k / 45.0,
                                             self.W["pinit"] * k / B, g_pose, loss, self.ws)
-        self._g_smpl = (g_trans, g_pose[:, :3], g_pose[:, 3:66], g_betas[:, :2], g_betas[:, 2:])
-        for p, g in zip(self.smpl_params, self._g_smpl):
-            p.grad = g
-        self.opt_smpl.step(self._g_smpl)
+        by_name = {"trans": g_trans, "global_pose": g_pose[:, :3], "body_pose": g_pose[:, 3:66], "hand_pose": g_pose[:, 66:],
+                   "top_betas": g_betas[:, :2], "other_betas": g_betas[:, 2:]}
+        self._g_smpl = tuple(by_name[n] for n in self.smpl_names)
+        self._g_pose_full = g_pose                                    # (B,156) incl. the hand-pose gradient (not optimised here)
+        self.opt_smpl.step(self._g_smpl, self.kdev, loss)
         return loss
 
     @torch.no_grad()
@@ -545,7 +618,7 @@ class FusedFitSteps:
         t, s = self.t.detach(), self.s.detach()
         obj = self.h_aux.rigid_fwd(obj0, Rm, t, s)
         (df, _, _, cen), _ = self.h_net.query_fwd(feat, skip, obj, self.cc, _lib.HEAD_DF | _lib.HEAD_CENTERS)
-        k = 1.0 / (1.0 + self.decay)
+        k = 1.0          # see smpl_step
         wc = self.W["ocent"] * k / B
         g_df, g_cen, dvec = self.h_aux.fit_obj_field_grads(obj, df, cen, d["smpl_center"], s, self.obj_scale, self.W["object"] * k / (B * N), wc,
                                                            self.W["scale"] * k / B, loss, self.ws)
@@ -554,10 +627,18 @@ class FusedFitSteps:
         g_R, g_t, g_s, _ = self.h_aux.rigid_bwd(obj0, Rm, t, s, g_obj, False)
         g_s.add_(s - self.obj_scale, alpha=self.W["scale"] * k * 2.0 / B)
         g_rot = self.h_aux.project_so3_bwd(rot_in, g_R)
-        self.R.grad, self.t.grad, self.s.grad = g_rot, g_t, g_s
-        self.opt_obj.step((g_t, g_rot, g_s))
+        self._g_obj = (g_t, g_rot, g_s)
+        self.opt_obj.step(self._g_obj, self.kdev, loss)
         return loss
 
     def graphed(self):
-        """(smpl_step, object_step) captured in CUDA graphs; each call replays one optimisation step."""
-        return GraphedStep(self.smpl_step), GraphedStep(self.object_step)
+        """(smpl_step, object_step) of the CURRENT phase captured in CUDA graphs; each call replays one optimisation
+        step.  The warm-up steps the capture needs are undone (parameters, Adam moments, accumulators, step counters), so
+        N replays apply exactly N updates.  zero_grad() / set_decay() act on device buffers the graphs read; after
+        set_phase('global' <-> others) capture again (the parameter set changes)."""
+        snap_s = lambda: (self.opt_smpl.state(), self.loss_smpl.clone())
+        rest_s = lambda st: (self.opt_smpl.load_state(st[0]), self.loss_smpl.copy_(st[1]))
+        snap_o = lambda: (self.opt_obj.state(), self.loss_obj.clone())
+        rest_o = lambda st: (self.opt_obj.load_state(st[0]), self.loss_obj.copy_(st[1]))
+        return (GraphedStep(self.smpl_step, snapshot=snap_s, restore=rest_s),
+                GraphedStep(self.object_step, snapshot=snap_o, restore=rest_o))

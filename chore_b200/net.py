@@ -86,7 +86,7 @@ class CHORE(nn.Module):
         if opt is not None:
             # the kernels are compiled for the chore-release configuration (config/chore-release.json)
             expect = {"z_feat": "xyz", "projection_mode": "perspective", "skip_hourglass": True, "num_stack": 5,
-                      "hourglass_dim": 256, "num_hourglass": 2, "norm": "group", "hg_down": "ave_pool"}
+                      "hourglass_dim": 256, "num_hourglass": 2, "norm": "group", "hg_down": "ave_pool", "loadSize": 1200}
             for k, v in expect.items():
                 got = getattr(opt, k, v)
                 assert got == v, f"chore_b200 is built for {k}={v!r}, the config asks for {got!r}"

@@ -222,7 +222,14 @@ int chore_surface_step(chore_handle *h, const float *points, const float *g_poin
                        float threshold, int B, int N, float *out_points, void *stream);
 
 /* torch.optim.Adam.step (weight_decay 0, amsgrad off) for up to CHORE_ADAM_MAX_ENTRIES small tensors in one
- * launch.  `step` is a device int32 step counter (read, then incremented by the kernel: graph-replay safe). */
+ * launch.  `step` is a device int32 step counter (read, then incremented by the kernel: graph-replay safe).
+ * The reference fitting loops call zero_grad() once per OUTER iteration and loss.backward() in every inner step
+ * (recon/recon_fit_behave.py:135-152,244-273), so the gradient Adam sees is the SUM of the inner-step gradients
+ * since the last zero_grad().  `grad_acc` (optional, per entry) reproduces that: acc += gscale * grad, Adam reads
+ * acc; the caller zeroes it where the reference calls zero_grad().  `gscale` (optional device scalar, default 1)
+ * is the 1 / (1 + decay) factor of get_loss_weights (:339-358) that multiplies every loss term: a captured graph
+ * follows the decay schedule by rewriting that scalar.  `loss_inout` (optional device scalar) is multiplied by
+ * gscale in the same launch so the reported loss carries the same factor. */
 #define CHORE_ADAM_MAX_ENTRIES 8
 typedef struct {
     float *param;            /* (rows, cols) contiguous                                   */
@@ -230,10 +237,11 @@ typedef struct {
                                 of a wider gradient buffer is fine)                       */
     float *exp_avg;          /* (rows, cols) contiguous state                             */
     float *exp_avg_sq;
+    float *grad_acc;         /* (rows, cols) contiguous accumulator, or NULL              */
     int rows, cols, grad_ld;
 } chore_adam_entry;
 int chore_adam_step(chore_handle *h, const chore_adam_entry *entries, int n, float lr, float beta1, float beta2,
-                    float eps, int32_t *step, void *stream);
+                    float eps, int32_t *step, const float *gscale, float *loss_inout, void *stream);
 
 #ifdef __cplusplus
 }

@@ -287,6 +287,100 @@ def gold_gen_pc_batch():
     save("gen_pc_batch.npz", seed_human=71, seed_object=72, num_points=25000, num_steps=10, **out)
 
 
+def strided(t, step):
+    """every `step`-th point (last axis) of a (B, C, N) / (B, 3, 3, N) prediction"""
+    return t[..., ::step]
+
+
+def gold_query_grid256(net):
+    """BASELINE config 2 at its real size: three x-planes (ix = 40, 128, 215; 3 x 65 536 points) of the 256^3 grid
+    create_grid(256, 256, 256, pmin, pmax) (model/sdf.py:4-27, bounds recon/generator.py:45-48) through CHORE.query.
+    df is stored for every point, the other heads on every 8th point + the part argmax of every point."""
+    install_sdf = ref_shim.install
+    install_sdf()
+    with ref_shim.ref_cwd():
+        from model.sdf import create_grid
+    sd = O.make_state_dict(0, "unit")
+    net.load_state_dict(sd)
+    feat, tmpx = O.synth_features(91, B=1)
+    net.im_feat_list, net.tmpx = [feat], tmpx
+    cc = torch.tensor([[1008., 995.]])
+    res = (256, 256, 256)
+    bmin, bmax = np.array([-3.0, -0.9, 0.2]), np.array([3.0, 1.8, 4.0])
+    coords, _ = create_grid(*res, bmin, bmax)
+    planes = (40, 128, 215)
+    pts = torch.from_numpy(np.concatenate([coords[:, ix].reshape(3, -1) for ix in planes], 1).T.copy()).float().unsqueeze(0)
+    with torch.no_grad():
+        net.query(pts, crop_center=cc)
+        df, pca, parts, centers = net.get_preds()
+    save("query_grid256.npz", seed=91, weights_seed=0, crop_center=cc, res=np.array(res), bmin=bmin, bmax=bmax,
+         planes=np.array(planes), df=df, parts_argmax=parts.argmax(1).to(torch.uint8), stride=8,
+         pca_s=strided(pca, 8), parts_s=strided(parts, 8), centers_s=strided(centers, 8),
+         top2_margin=(parts.topk(2, dim=1).values[:, 0] - parts.topk(2, dim=1).values[:, 1]).half(),
+         feat_ck=checksum(feat), tmpx_ck=checksum(tmpx))
+
+
+def gold_query_b32(net):
+    """BASELINE config 4 batch shape: 32 images x 1 024 points in ONE CHORE.query call (per-image crop centres)."""
+    sd = O.make_state_dict(0, "unit")
+    net.load_state_dict(sd)
+    B, N = 32, 1024
+    feat, tmpx = O.synth_features(95, B=B, hw=64)        # 256 x 256 inputs: 32 full-size maps would be 2 GB of fixtures to regenerate
+    net.im_feat_list, net.tmpx = [feat], tmpx
+    g = torch.Generator().manual_seed(96)
+    cc = torch.tensor([[1008., 995.]]) + 40 * torch.randn(B, 2, generator=g)
+    pts = torch.cat([O.synth_points("init_box", 97, B, N // 2), O.synth_points("frustum", 98, B, N // 2, cc)], 1)
+    with torch.no_grad():
+        net.query(pts, crop_center=cc)
+        df, pca, parts, centers = net.get_preds()
+    save("query_b32.npz", seed=95, weights_seed=0, crop_center=cc, points_ck=checksum(pts), df=df,
+         parts_argmax=parts.argmax(1).to(torch.uint8), stride=8, pca_s=strided(pca, 8), parts_s=strided(parts, 8),
+         centers_s=strided(centers, 8), feat_ck=checksum(feat))
+
+
+def gold_testdata_example(net):
+    """The shipped demo frame (example/000000117377/k1.*) through the reference's TestData.prepare_image_crop
+    (data/test_data.py:59-125) and then through CHORE.filter: the realistic (non white-noise) input of the suite.
+    The frame itself is committed under tests/golden/example_frame/ (data fixture of the reference, 425 kB)."""
+    import shutil, tempfile
+    TestData = ref_shim.load_testdata_class()
+    tmp = tempfile.mkdtemp()
+    src = os.path.join(ref_shim.REF_ROOT, "example", "000000117377")
+    for f in os.listdir(src):
+        shutil.copy(os.path.join(src, f), tmp)
+    rgb = os.path.join(tmp, "k1.color.jpg")
+    out = {}
+    for mean_center in (False, True):
+        ds = TestData([rgb], 1, 0, image_size=(512, 512), crop_size=1200, use_mean_center=mean_center)
+        item = ds.get_item(0)
+        tag = "mc" if mean_center else "own"
+        out[f"images_{tag}_s4"] = item["images"][:, ::4, ::4]
+        out[f"images_{tag}_ck"] = checksum(torch.from_numpy(item["images"]))
+        out[f"crop_center_{tag}"] = item["crop_center"]
+        out[f"old_crop_center_{tag}"] = np.asarray(item["old_crop_center"])
+        out[f"resize_scale_{tag}"] = item["resize_scale"]
+        out[f"crop_scale_{tag}"] = item["crop_scale"]
+        if not mean_center:
+            import pickle as pkl
+            info = pkl.load(open(rgb.replace(".color.jpg", ".crop_info.pkl"), "rb"))
+            out.update({f"crop_info_{k}": np.asarray(v) for k, v in info.items()})
+            images = torch.from_numpy(item["images"]).unsqueeze(0)
+    sd = O.make_state_dict(0, "unit")
+    net.load_state_dict(sd)
+    with torch.no_grad():
+        net.filter(images)
+        feat, tmpx = net.im_feat_list[-1], net.tmpx
+    # a fitting-style query on the real-image features: SMPL-like points around the person at z0
+    cc = torch.from_numpy(out["crop_center_own"]).float().unsqueeze(0)
+    pts = O.synth_points("frustum", 99, 1, 2048, cc)
+    with torch.no_grad():
+        net.query(pts, crop_center=cc)
+        df, pca, parts, centers = net.get_preds()
+    save("example_frame.npz", weights_seed=0, feat_s8=feat[:, :, ::8, ::8], tmpx_s8=tmpx[:, :, ::8, ::8], feat_ck=checksum(feat),
+         tmpx_ck=checksum(tmpx), points=pts, df=df, pca=pca, parts=parts, centers=centers, **out)
+    shutil.rmtree(tmp)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
@@ -301,7 +395,19 @@ def main():
         gold_rigid_and_fit(net)
         gold_fit_smpl_full(net)
         gold_gen_pc_batch()
+        gold_query_grid256(net)
+        gold_query_b32(net)
+        gold_testdata_example(net)
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1:          # python -m oracle.make_golden gold_query_b32 ...: regenerate selected files only
+        torch.manual_seed(0)
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
+        net, _ = ref_shim.load_chore()
+        with ref_shim.ref_cwd():
+            for name in sys.argv[1:]:
+                fn = globals()[name]
+                fn() if name in ("gold_lbs", "gold_gen_pc_batch") else fn(net)
+    else:
+        main()

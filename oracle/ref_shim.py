@@ -123,6 +123,25 @@ def load_fitter_class():
     return ReconFitterBehave
 
 
+def load_testdata_class():
+    """The reference's TestData (data/test_data.py).  psbody.mesh is stubbed, so `load_mocap_mesh` (the only Mesh use on
+    this path, test_data.py:213-217) is replaced by a numpy read of the binary PLY vertex block."""
+    install()
+    import numpy as np
+    with ref_cwd(), contextlib.redirect_stdout(open(os.devnull, "w")):
+        from data.test_data import TestData
+
+    def load_mocap_mesh(self, rgb_file):
+        raw = open(rgb_file.replace(".color.jpg", ".mocap.ply"), "rb").read()
+        head, body = raw.split(b"end_header\n", 1)
+        n = int([l for l in head.decode().splitlines() if l.startswith("element vertex")][0].split()[-1])
+        assert b"binary_little_endian" in head and b"property float x" in head
+        return types.SimpleNamespace(v=np.frombuffer(body[:n * 12], dtype="<f4").reshape(n, 3).astype(np.float64))
+
+    TestData.load_mocap_mesh = load_mocap_mesh
+    return TestData
+
+
 def load_generator_class():
     install()
     with ref_cwd(), contextlib.redirect_stdout(open(os.devnull, "w")):

@@ -457,12 +457,105 @@ def test_fused_fit_steps_match_autograd_path(net, smpl_layer):
         assert rel_err(a.grad, b.grad) < 1e-4, (name, rel_err(a.grad, b.grad))
     # CUDA-graph replay: the loss decreases over 30 replayed Adam steps
     sg = mk(); Rg, tg, scg = mkobj()
-    g_smpl, g_obj = chore_b200.FusedFitSteps(net, sg, data, Rg, tg, scg, lr_smpl=0.006, lr_obj=0.006).graphed()
+    # (plain Adam here: with the reference's accumulate-over-10-steps gradients the loss of a white-noise field need not go
+    # down monotonically; that loop shape is pinned against the autograd path in test_fused_fit_loop_matches_reference_loop_semantics)
+    fused_g = chore_b200.FusedFitSteps(net, sg, data, Rg, tg, scg, lr_smpl=0.006, lr_obj=0.006, accumulate=False)
+    g_smpl, g_obj = fused_g.graphed()
     first = (float(g_smpl()), float(g_obj()))
-    for _ in range(30):
+    for i in range(30):
         g_smpl(); g_obj()
     last = (float(g_smpl()), float(g_obj()))
     assert last[0] < first[0] and last[1] < first[1], (first, last)
+
+
+def test_fused_adam_matches_torch_adam_with_accumulation():
+    """chore_adam_step against torch.optim.Adam over 12 steps in the reference's loop shape: zero_grad() once per outer
+    iteration, gradients ADD UP over the inner steps (recon/recon_fit_behave.py:135-152,244-273), every gradient scaled by
+    1 / (1 + decay) with a decay that changes per outer iteration."""
+    import chore_b200
+    gen = torch.Generator().manual_seed(5)
+    shapes = [(2, 3), (2, 63), (2,), (2, 3, 3)]
+    p_ref = [torch.randn(*sh, generator=gen).to(DEV).requires_grad_(True) for sh in shapes]
+    p_fus = [p.detach().clone().requires_grad_(True) for p in p_ref]
+    opt = torch.optim.Adam(p_ref, lr=0.006)
+    fused = chore_b200.FusedAdam(p_fus, lr=0.006, accumulate=True)
+    kdev = torch.ones(1, device=DEV)
+    for outer in range(3):
+        opt.zero_grad(); fused.zero_grad()
+        k = 1.0 / (1.0 + outer / 3)
+        kdev.fill_(k)
+        for inner in range(4):
+            grads = [torch.randn(*sh, generator=gen).to(DEV) for sh in shapes]
+            for p, g in zip(p_ref, grads):
+                p.grad = (p.grad if p.grad is not None else torch.zeros_like(p)) + k * g
+            opt.step()
+            fused.step(grads, kdev)
+            for a, b in zip(p_fus, p_ref):
+                assert rel_err(a, b) < 1e-5, (outer, inner, rel_err(a, b))
+                assert rel_err(a.grad, b.grad) < 1e-5
+
+
+def test_fused_fit_loop_matches_reference_loop_semantics(net, smpl_layer):
+    """FusedFitSteps driven like optimize_smpl / optimize_smpl_object drive their step (zero_grad per outer iteration,
+    accumulating .grad, decay = it / 3 in phase 'kpts', torch.optim.Adam) == the autograd path run in that same loop:
+    the parameters after 2 outer x 3 inner steps agree, eagerly and replayed from CUDA graphs (whose warm-up must not
+    leave extra updates behind)."""
+    import chore_b200
+    g = load_golden("fit_smpl_full.npz")
+    fit, w, data, _ = _smpl_full_setup(net, smpl_layer, g)
+    gen = torch.Generator().manual_seed(19)
+    obj = (0.2 * torch.randn(2, 3000, 3, generator=gen)).to(DEV)
+    noise = torch.rand(2, 3, 3, generator=gen).to(DEV)
+    data.update({"objects": obj, "smpl_center": torch.tensor([[0.0, 0.1, 2.2], [0.0, 0.0, 2.2]], device=DEV)})
+    mkobj = lambda: ((torch.eye(3).repeat(2, 1, 1) + 0.05 * torch.randn(2, 3, 3, generator=torch.Generator().manual_seed(3))).to(DEV).requires_grad_(True),
+                     torch.tensor([[0.2, 0.1, 2.3], [0.1, 0.0, 2.2]], device=DEV, requires_grad=True), torch.ones(2, device=DEV, requires_grad=True))
+    names = ("trans", "global_pose", "body_pose", "top_betas", "other_betas")
+    wd = fit.get_loss_weights()
+    outer_iters, inner = (3, 6), 3          # 'kpts' iterations it = 3 and 6: decay 1 and 2
+
+    # reference-shaped loop on the autograd path
+    sa = fit.split_smpl(w); Ra, ta, sca = mkobj()
+    opt_s = torch.optim.Adam([getattr(sa, n) for n in names], 0.006)
+    opt_o = torch.optim.Adam([ta, Ra, sca], lr=0.006)
+    for it in outer_iters:
+        opt_s.zero_grad(); opt_o.zero_grad()
+        for _ in range(inner):
+            fit.sum_dict(fit.forward_smpl(sa, data, "kpts"), wd, it / 3).backward(); opt_s.step()
+            fit.sum_dict(fit.forward_step(net, sa, data, Ra, ta, sca, "object only", noise=noise), wd, it / 3).backward(); opt_o.step()
+
+    def run(graphed):
+        sf = fit.split_smpl(w); Rf, tf, scf = mkobj()
+        fused = chore_b200.FusedFitSteps(net, sf, data, Rf, tf, scf, fitter=fit, phase="kpts")
+        s_step, o_step = fused.graphed() if graphed else (fused.smpl_step, lambda: fused.object_step(noise))
+        if graphed:                          # the captured object step draws its own noise: pin it for the comparison
+            o_step = lambda: fused.object_step(noise)
+        for it in outer_iters:
+            fused.zero_grad(); fused.set_decay(it / 3)
+            for _ in range(inner):
+                s_step(); o_step()
+        return sf, (Rf, tf, scf)
+
+    for graphed in (False, True):
+        sf, (Rf, tf, scf) = run(graphed)
+        # 6 chained Adam steps through clamp / ReLU gates: looser than one step, far tighter than an extra or a missing update
+        for n in names:
+            assert rel_err(getattr(sf, n), getattr(sa, n)) < 2e-3, (graphed, n, rel_err(getattr(sf, n), getattr(sa, n)))
+        for a, b, n in ((Rf, Ra, "R"), (tf, ta, "t"), (scf, sca, "s")):
+            assert rel_err(a, b) < 2e-3, (graphed, n, rel_err(a, b))
+    # the 'global' phase of optimize_smpl: only top_betas and trans move, lr 0.02
+    sg = fit.split_smpl(w); Rg, tg, scg = mkobj()
+    fused = chore_b200.FusedFitSteps(net, sg, data, Rg, tg, scg, fitter=fit, phase="global")
+    before = {n: getattr(sg, n).detach().clone() for n in names + ("hand_pose",)}
+    fused.zero_grad(); fused.smpl_step()
+    assert not torch.equal(sg.trans, before["trans"]) and not torch.equal(sg.top_betas, before["top_betas"])
+    for n in ("global_pose", "body_pose", "hand_pose", "other_betas"):
+        assert torch.equal(getattr(sg, n), before[n]), n
+    # the full pose gradient (incl. the hand pose, which carries the hand prior) matches autograd
+    sh = fit.split_smpl(w)
+    fit.sum_dict(fit.forward_smpl(sh, data, "kpts"), wd, 1).backward()
+    fh = chore_b200.FusedFitSteps(net, fit.split_smpl(w), data, Rg, tg, scg, lr_smpl=0.0, fitter=fit, phase="kpts")
+    fh.set_decay(1); fh.smpl_step()
+    assert rel_err(0.5 * fh._g_pose_full[:, 66:], sh.hand_pose.grad) < 1e-4, rel_err(0.5 * fh._g_pose_full[:, 66:], sh.hand_pose.grad)
 
 
 def test_generator_gen_pc_batch_mechanics(net):
