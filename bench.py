@@ -9,13 +9,23 @@ One step (own arm) = the hot path over one image: hourglass encoder on a 5x512x5
 full field (4 heads, 31 channels) on the 256^3 dense grid of BASELINE.json configs[1]
 (model/sdf.py:create_grid semantics over Generator.pmin/pmax).  `value` = grid points / step time
 with the image resident in HBM; `e2e` = the same through the public API (`CHORE.filter` +
-`Generator.eval_grid`) with the image copied from pinned host memory and the distance field copied
-back every step.  At N > 1 every rank processes its own image + grid (weak scaling); the only
-collective is an NCCL all-gather of a per-image summary.
+`Generator.eval_grid`) with the image copied from pinned host memory and the distance field (the 2 df
+channels eval_grid's caller reads, 134 MB of the 2.08 GB field) copied back chunk by chunk on a side
+stream while the next chunk computes.  At N > 1 every rank processes its own image + grid (weak
+scaling); the only collective is an NCCL all-gather of a per-image summary.
+
+Beside the headline the same JSON line carries
+  image20k  the north-star per-image workload: 512x512 image + 20 000 query points, 4 heads -- points/s including the
+            encoder (device-timed and end to end), the encoder's own tensor roofline, and a CPU leg of the same;
+  fit       fit-iterations/s (SMPL-H step + object-only step, 20 k object samples, Adam; every rank runs its own
+            problem, the value is the sum over ranks) with the CPU port of the same iteration timed in the same run;
+  strong    (N > 1) ONE image, the 256^3 grid point-sharded over the ranks, df all-gathered over NCCL.
 
 The reference arm times the CPU restatement of the reference's own PyTorch path (oracle/, kind
-"port": the reference is Python and /root/reference does not exist on the GPU box) on a bounded
-sample of the same workload, with all host threads.
+"port": the reference is Python and /root/reference does not exist on the GPU box) with all host
+threads: the encoder once and a bounded slab of the grid, timed SEPARATELY, and composes the value of
+the full workload from them (encoder_s + 16 777 216 / query_points_per_s), so both arms quote the same
+configuration.
 """
 from __future__ import annotations
 
@@ -42,6 +52,15 @@ BYTES_PER_POINT_GRID = 31 * 4                             # grid mode: coordinat
 CHUNK = 1 << 22                                           # points per launch
 WORKLOAD = "1x 5x512x512 image -> hourglass encoder -> 256^3 dense grid, 4 heads (31 ch)"
 METRIC = "query_points_per_sec"
+ENC_FLOP = 258.25e9                                        # conv2d MACs x 2 of one 512 x 512 image
+
+
+def workload_config(world: int) -> dict:
+    """The `config` object: identical in both arms (same workload, same sizes)."""
+    return {"workload": WORKLOAD, "points_per_step_per_gpu": RES[0] * RES[1] * RES[2], "chunk": CHUNK,
+            "l2": "256 MiB flush between timed iterations (untimed); outputs 2.08 GB/step > L2",
+            "weights": "seeded synthetic (unit gain), chore-release shapes",
+            "parallelism": f"{world}x independent image+grid (weak), NCCL all-gather of summaries"}
 
 
 def peaks():
@@ -99,12 +118,16 @@ class ClockSampler:
 # =====================================================================================================
 # reference arm / cpu baseline: the oracle (CPU restatement of the reference's PyTorch path)
 # =====================================================================================================
-def cpu_step(sd, img, cc, n_points, start=0):
-    """encoder + field on `n_points` consecutive grid points (batch_eval chunks of 32768)."""
-    import numpy as np
+def cpu_encode(sd, img):
     from oracle import chore_oracle as O
     with torch.no_grad():
-        feat, tmpx = O.encode(sd, img)
+        return O.encode(sd, img)
+
+
+def cpu_query_slab(sd, feat, tmpx, cc, n_points, start=0):
+    """the field on `n_points` consecutive grid points (batch_eval chunks of 32768, model/sdf.py:30-41)."""
+    from oracle import chore_oracle as O
+    with torch.no_grad():
         step = [(PMAX[i] - PMIN[i]) / RES[i] for i in range(3)]
         acc = 0.0
         for s in range(start, start + n_points, 32768):
@@ -117,6 +140,83 @@ def cpu_step(sd, img, cc, n_points, start=0):
     return acc
 
 
+def cpu_sample(sd, img, cc, n_points, start):
+    """One bounded sample of the workload on the CPU: (encoder seconds, slab-query seconds)."""
+    t0 = time.perf_counter()
+    feat, tmpx = cpu_encode(sd, img)
+    t1 = time.perf_counter()
+    cpu_query_slab(sd, feat, tmpx, cc, n_points, start)
+    return t1 - t0, time.perf_counter() - t1
+
+
+def compose_cpu(enc_s, q_s, n_points):
+    """Full-workload figure from the two separately timed parts: one encoder pass + the whole grid at the slab's rate."""
+    total = RES[0] * RES[1] * RES[2]
+    rate = n_points / q_s
+    full_s = enc_s + total / rate
+    return {"value": total / full_s, "encoder_s": enc_s, "query_points_per_s": rate, "full_step_s_extrapolated": full_s}
+
+
+def cpu_image20k(sd, cc, reps=2):
+    """The north-star per-image workload on the CPU: encoder + one 20 000-point query of all heads."""
+    from oracle import chore_oracle as O
+    img = O.synth_images(0, B=1, size=512)
+    pts = O.synth_points("init_box", 5, 1, 20000)
+    with torch.no_grad():
+        feat, tmpx = O.encode(sd, img)
+        O.query(sd, feat, tmpx, pts, cc)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            feat, tmpx = O.encode(sd, img)
+            t1 = time.perf_counter()
+            O.query(sd, feat, tmpx, pts, cc)
+        dt = (time.perf_counter() - t0) / reps
+    return {"value": 20000 / dt, "unit": "points/s", "s_per_image": dt, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{reps} x (encoder + 20000-point query, 4 heads), torch CPU fp32"}
+
+
+def cpu_fit_iteration(sd, steps=3, n_obj=20000):
+    """One fit iteration of bench_fit.make_fit_problem's shape on the CPU port: SMPL-H step (LBS, landmarks, 6890-vertex
+    query, every forward_smpl term of phase 'kpts', backward, Adam) + object-only step (SO(3), rigid, 2 x 20k-point query
+    as the reference does, backward, Adam)."""
+    from oracle import chore_oracle as O
+    g = torch.Generator().manual_seed(7)
+    feat, tmpx = O.synth_features(3, B=1)
+    model = O.make_smplh_buffers(0)
+    cc = torch.tensor([[1008., 995.]])
+    regs = [torch.zeros(L, 6890).scatter_(1, torch.randint(6890, (L, 270), generator=g), 1.0 / 270) for L in (25, 70, 42)]
+    pri = {"body_mean": 0.1 * torch.randn(63, generator=g), "body_prec": torch.eye(63), "hand_mean": 0.1 * torch.randn(90, generator=g),
+           "lh_prec": torch.eye(45), "rh_prec": torch.eye(45)}
+    pose = (0.1 * torch.randn(1, 156, generator=g)).requires_grad_(True)
+    betas = (0.3 * torch.randn(1, 10, generator=g)).requires_grad_(True)
+    trans = torch.tensor([[0.0, 0.1, 2.2]], requires_grad=True)
+    labels = torch.randint(14, (1, 6890), generator=g)
+    pose_init = pose.detach()[:, 3:72].clone()
+    kpts = torch.cat([512 * torch.rand(1, 25, 2, generator=g), torch.rand(1, 25, 1, generator=g)], -1)
+    obj = 0.2 * torch.randn(1, n_obj, 3, generator=g)
+    R = (torch.eye(3).unsqueeze(0) + 0.05 * torch.randn(1, 3, 3, generator=g)).requires_grad_(True)
+    t = torch.tensor([[0.2, 0.1, 2.3]], requires_grad=True)
+    sc = torch.ones(1, requires_grad=True)
+    opt_s, opt_o = torch.optim.Adam([pose, betas, trans], 0.006), torch.optim.Adam([t, R, sc], 0.006)
+    center = torch.tensor([[0.0, 0.1, 2.2]])
+
+    def one():
+        opt_s.zero_grad()
+        O.sum_dict(O.smpl_full_losses(sd, feat, tmpx, cc, model, pose, betas, trans, labels, pose_init, regs, pri, kpts), 1).backward()
+        opt_s.step()
+        opt_o.zero_grad()
+        O.sum_dict(O.object_only_losses(sd, feat, tmpx, cc, obj, O.decopose_axis(R), t, sc, center), 1).backward()
+        opt_o.step()
+
+    one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": 1.0 / dt, "unit": "fit-iterations/s", "s_per_iteration": dt, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{steps} iterations, B=1, 6890 SMPL-H vertices + {n_obj} object samples, torch CPU fp32 autograd"}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -127,23 +227,27 @@ def run_reference(args, rank):
     img = O.synth_images(0, B=1, size=512)
     cc = torch.tensor([[1008., 995.]])
     n = args.cpu_points
+    total = RES[0] * RES[1] * RES[2]
     start = RES[1] * RES[2] * (RES[0] // 2)         # a slab through the middle of the volume
-    for _ in range(args.warmup):
-        cpu_step(sd, img, cc, n, start)
-    times = []
+    for _ in range(max(1, args.warmup)):
+        cpu_sample(sd, img, cc, n, start)
+    enc, qry = [], []
     for _ in range(args.steps):
-        t0 = time.perf_counter()
-        cpu_step(sd, img, cc, n, start)
-        times.append(time.perf_counter() - t0)
-    ms = 1e3 * sum(times) / len(times)
-    v = n / (ms / 1e3)
-    sample = f"encoder + {n} of {RES[0] * RES[1] * RES[2]} grid points per step (mid-volume slab), torch CPU fp32, {torch.get_num_threads()} threads"
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": sample},
-            "cpu_baseline": {"value": v, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        e, q = cpu_sample(sd, img, cc, n, start)
+        enc.append(e); qry.append(q)
+    enc_s, q_s = sum(enc) / len(enc), sum(qry) / len(qry)
+    comp = compose_cpu(enc_s, q_s, n)
+    sample = (f"per step: one encoder pass ({enc_s:.3f} s) + {n} of {total} grid points (mid-volume slab, {q_s:.3f} s), timed separately; "
+              f"value = {total} / (encoder_s + {total} / query_points_per_s); torch CPU fp32, {torch.get_num_threads()} threads")
+    line = {"impl": "reference", "metric": METRIC, "value": comp["value"], "unit": "points/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": max(1, args.warmup), "ms_per_step": 1e3 * (enc_s + q_s), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": comp["value"], "unit": "points/s", "cores": cores, "kind": "port", "sample": sample,
+                             "encoder_s": enc_s, "query_points_per_s": comp["query_points_per_s"],
+                             "full_step_s_extrapolated": comp["full_step_s_extrapolated"]},
+            "e2e": {"value": comp["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "image20k": {"cpu_baseline": cpu_image20k(sd, cc)},
+            "fit": {"cpu_baseline": cpu_fit_iteration(sd)} if not args.no_fit else None}
     print(json.dumps(line), flush=True)
 
 
@@ -153,27 +257,34 @@ def run_reference(args, rank):
 def fit_iteration_bench(net, dev, iters=300):
     """fit-iters/sec (BASELINE configs[2] shape): one iteration = SMPL-phase step (LBS -> landmarks -> query 6890 verts ->
     every forward_smpl term of phase 'kpts': df_h, pose/hand priors, part CE, smplz, pinit, j2d -> adjoints -> Adam) +
-    'object only' step (SO(3) -> rigid 20k samples -> query -> object/scale/ocent -> adjoints -> Adam).
+    'object only' step (SO(3) -> rigid 20k samples -> query -> object/scale/ocent -> adjoints -> Adam), driven like the
+    reference loops drive it: zero_grad() once per outer iteration of 10 steps, gradients accumulating in between.
     Headline: FusedFitSteps replayed from CUDA graphs (no autograd graph, no host sync); beside it the same step through
     the autograd-Function path (what an unmodified reference loop drives: forward_smpl / forward_step + backward)."""
     from bench_fit import make_fit_problem
     fit, cc, build_state = make_fit_problem(net, dev, 1, 20000, seed=7)
 
-    def timed(fn, n):
+    def timed(fn, n, every10=None):
         for _ in range(5):
             fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(n):
+        for i in range(n):
+            if every10 is not None and i % 10 == 0:
+                every10()
             fn()
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n
 
     split, (R, t, s), fused = build_state()
+    l0 = chore_launches()
+    fused.smpl_step(); fused.object_step()           # eager once: counts the kernels one replayed iteration launches
+    launches_per_iter = chore_launches() - l0
+    split, (R, t, s), fused = build_state()
     g_smpl, g_obj = fused.graphed()
-    ms_graph = timed(lambda: (g_smpl(), g_obj()), iters)
+    ms_graph = timed(lambda: (g_smpl(), g_obj()), iters, every10=fused.zero_grad)
     # the autograd-Function path
     split, (R, t, s), fused = build_state()
     data = fused.data
@@ -183,23 +294,47 @@ def fit_iteration_bench(net, dev, iters=300):
     noise = torch.rand(1, 3, 3).to(dev)
 
     def one():
-        opt_s.zero_grad()
         fit.sum_dict(fit.forward_smpl(split, data, "kpts"), w, 1).backward()
         opt_s.step()
-        opt_o.zero_grad()
         fit.sum_dict(fit.forward_step(net, split, data, R, t, s, "object only", noise=noise), w, 1).backward()
         opt_o.step()
 
-    ms_eager = timed(one, max(10, iters // 6))
+    ms_eager = timed(one, max(10, iters // 6), every10=lambda: (opt_s.zero_grad(), opt_o.zero_grad()))
     return {"fit_iters_per_sec": 1e3 / ms_graph, "ms_per_iter": ms_graph, "iters": iters,
-            "autograd_path_iters_per_sec": 1e3 / ms_eager,
+            "autograd_path_iters_per_sec": 1e3 / ms_eager, "kernel_launches_per_iteration": int(launches_per_iter),
             "iteration": "SMPL-H step (LBS + landmarks + query 6890 verts; df_h, pose/hand priors, part CE, smplz, pinit, j2d) + "
-                         "object-only step (SO3 + rigid 20k pts + query; object/scale/ocent), Adam, B=1; fused loss/adjoint/Adam "
-                         "kernels replayed from CUDA graphs"}
+                         "object-only step (SO3 + rigid 20k pts + query; object/scale/ocent), Adam on gradients accumulated since "
+                         "the last zero_grad() (every 10 steps, as recon_fit_behave.py does), B=1; fused loss/adjoint/Adam kernels "
+                         "replayed from CUDA graphs"}
+
+
+def chore_launches():
+    import chore_b200
+    return chore_b200.launch_count()
+
+
+def traffic_for(kernel_name):
+    """DRAM bytes per launch of `kernel_name` from the committed ncu capture, valid only for the kernel source it was
+    taken from (profiles/traffic.json carries the sha256 of that source file)."""
+    import hashlib
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        ent = t.get(kernel_name)
+        if isinstance(ent, dict):
+            src = os.path.join(ROOT, ent["source"])
+            sha = hashlib.sha256(open(src, "rb").read()).hexdigest()[:16]
+            if sha != ent.get("source_sha16"):
+                return None, f"stale: {ent['source']} changed since the ncu capture {ent.get('capture')}"
+            return ent["dram_bytes_per_launch"], ent.get("capture")
+        return ent, "profiles/traffic.json (unkeyed)"
+    except Exception as e:
+        return None, f"unavailable: {e}"
 
 
 def run_ours(args, rank, world, local_rank):
     import chore_b200
+    from chore_b200 import dist as cdist
     from oracle import chore_oracle as O            # input / weight synthesis + the cpu_baseline leg only
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
@@ -217,14 +352,21 @@ def run_ours(args, rank, world, local_rank):
     img_dev = img_host.to(dev)
     cc = torch.tensor([[1008., 995.]], device=dev)
     outs = [torch.empty(c, total, device=dev) for c in (2, 9, 14, 6)]
-    df_host = torch.empty(2, total).pin_memory()
+    df_host = torch.empty((total + CHUNK - 1) // CHUNK, 2, CHUNK).pin_memory()      # per chunk: (2, CHUNK) contiguous
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
     handle = net.handle
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    q_events = []
+    q_events, enc_events = [], []
+    copy_stream = torch.cuda.Stream(device=dev)
 
     def step_device(record):
+        if record:
+            a, b = ev(), ev()
+            a.record()
         feat, skip, _ = handle.encode(img_dev, want_normx=False)
+        if record:
+            b.record()
+            enc_events.append((a, b))
         for start in range(0, total, CHUNK):
             if record:
                 a, b = ev(), ev()
@@ -235,10 +377,21 @@ def run_ours(args, rank, world, local_rank):
                 q_events.append((a, b, min(CHUNK, total - start)))
 
     def step_e2e():
+        """CHORE.filter + the dense field through the public API; the df channels of chunk k travel to the host on a side
+        stream while chunk k+1 computes (Generator.eval_grid semantics: the caller reads df)."""
         img = img_host.to(dev, non_blocking=True)
         net.filter(img)
-        res = gen.eval_grid(RES, cc, 0, head_mask=15, chunk=CHUNK)
-        df_host.copy_(res[0].view(2, -1), non_blocking=True)
+        main = torch.cuda.current_stream()
+        for start in range(0, total, CHUNK):
+            n = min(CHUNK, total - start)
+            gen.eval_grid_chunk(RES, cc, 0, start, n, outs, head_mask=15)
+            done = ev()
+            done.record(main)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done)
+                for ch in range(2):        # row slices are contiguous on both sides: plain async DMA
+                    df_host[start // CHUNK, ch, :n].copy_(outs[0][ch, start:start + n], non_blocking=True)
+        main.wait_stream(copy_stream)
 
     def timed(fn, steps, **kw):
         durations = []
@@ -258,6 +411,18 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    def sum_over_ranks(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.item()
+
     for _ in range(max(3, args.warmup)):
         step_device(False)
     barrier()
@@ -271,43 +436,117 @@ def run_ours(args, rank, world, local_rank):
     if dist is not None:
         gathered = [torch.empty_like(summary) for _ in range(world)]
         dist.all_gather(gathered, summary)
-    step_ms = torch.tensor([sum(ms_steps)], device=dev, dtype=torch.float64)
     for _ in range(3):
         step_e2e()
     barrier()
     ms_e2e = timed(step_e2e, args.steps)
-    e2e_ms = torch.tensor([sum(ms_e2e)], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    ms_per_step = step_ms.item() / args.steps
+    ms_per_step = max_over_ranks(sum(ms_steps)) / args.steps
+    e2e_ms_per_step = max_over_ranks(sum(ms_e2e)) / args.steps
     value = world * total / (ms_per_step / 1e3)
-    e2e_value = world * total / (e2e_ms.item() / args.steps / 1e3)
+    e2e_value = world * total / (e2e_ms_per_step / 1e3)
+    barrier()
+
+    # ---- north-star per-image workload: 512 x 512 image + 20 000 query points, 4 heads ------------------------------
+    pts_host = O.synth_points("init_box", 5 + rank, 1, 20000).pin_memory()
+    pts_dev = pts_host.to(dev)
+    out20_host = torch.empty(31, 20000).pin_memory()
+
+    def image20k_device():
+        feat, skip, _ = handle.encode(img_dev, want_normx=False)
+        handle.query_fwd(feat, skip, pts_dev, cc, 15)
+
+    def image20k_e2e():
+        net.filter(img_host.to(dev, non_blocking=True))
+        net.query(pts_host.to(dev, non_blocking=True), crop_center=cc)
+        df, pca, parts, centers = net.get_preds()
+        out20_host.copy_(torch.cat([df[0], pca.reshape(1, 9, -1)[0], parts[0], centers[0]], 0), non_blocking=True)
+
+    for _ in range(3):
+        image20k_device(); image20k_e2e()
+    barrier()
+    reps20 = max(10, args.steps)
+    ms20 = max_over_ranks(sum(timed(image20k_device, reps20))) / reps20
+    ms20_e2e = max_over_ranks(sum(timed(image20k_e2e, reps20))) / reps20
+    barrier()
+
+    # ---- fit iterations: every rank its own problem, summed ------------------------------------------------------------
+    fit = None
+    if not args.no_fit:
+        fit = fit_iteration_bench(net, str(dev))
+        fit["fit_iters_per_sec_per_gpu"] = fit["fit_iters_per_sec"]
+        fit["fit_iters_per_sec"] = sum_over_ranks(fit["fit_iters_per_sec"])
+        fit["n_gpus"] = world
+        barrier()
+
+    # ---- strong scaling: ONE image, the grid point-sharded over the ranks, df all-gathered ------
+    strong = None
+    if dist is not None:
+        start, count = cdist.shard_range(total)
+        counts = [cdist.shard_range(total, r, world)[1] for r in range(world)]
+        img0 = O.synth_images(0, B=1, size=512).to(dev)            # every rank encodes the SAME image (cheaper than a broadcast)
+        assert len(set(counts)) == 1, "256^3 / 128 tiles divide evenly over 2, 4 and 8 ranks"
+        gath = torch.empty(world, 2, count, device=dev)            # rank r's slab of df: gath[r] = df[:, r*count:(r+1)*count]
+
+        def strong_step(ag_events=None):
+            feat, skip, _ = handle.encode(img0, want_normx=False)
+            for s0 in range(start, start + count, CHUNK):
+                handle.query_grid(feat, skip, cc, 0, RES, PMIN, PMAX, s0, min(CHUNK, start + count - s0), 15, outs)
+            local = outs[0][:, start:start + count].contiguous()
+            if ag_events is not None:
+                a = ev(); a.record()
+            dist.all_gather_into_tensor(gath.view(-1), local.view(-1))
+            if ag_events is not None:
+                b = ev(); b.record(); ag_events.append((a, b))
+
+        for _ in range(3):
+            strong_step()
+        barrier()
+        ag = []
+        ms_strong = max_over_ranks(sum(timed(strong_step, args.steps, ag_events=ag))) / args.steps
+        torch.cuda.synchronize()
+        ag_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ag)) / args.steps
+        strong = {"value": total / (ms_strong / 1e3), "unit": "points/s", "ms_per_step": ms_strong, "scaling": "strong",
+                  "allgather_ms": ag_ms, "allgather_bytes_per_rank": 8 * count, "points_per_rank": count,
+                  "workload": "ONE 5x512x512 image encoded on every rank, 256^3 grid in contiguous 128-aligned shards, 4 heads, "
+                              "df (2 ch) all-gathered over NCCL"}
+        barrier()
 
     if rank == 0:
         pk = peaks()
         q_ms = [a.elapsed_time(b) for a, b, _ in q_events]
         q_pts = [n for _, _, n in q_events]
+        enc_ms = [a.elapsed_time(b) for a, b in enc_events]
         avg_ms = sum(q_ms) / len(q_ms)
+        avg_enc_ms = sum(enc_ms) / len(enc_ms)
         flops = FLOP_PER_POINT * (sum(q_pts) / len(q_pts))
         bytes_ = MAP_BYTES + BYTES_PER_POINT_GRID * (sum(q_pts) / len(q_pts))
         tf = flops / (avg_ms / 1e3) / 1e12
+        traffic, traffic_src = traffic_for(args.kernel_name)
         roofline = {"kernel": args.kernel_name, "bound": "tensor", "achieved": tf, "peak": pk["bf16"], "unit": "TFLOP/s",
-                    "frac": tf / pk["bf16"], "traffic": None, "peak_source": pk["src"] + " bf16 dense (burst)",
+                    "frac": tf / pk["bf16"], "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": pk["src"] + " bf16 dense (burst)",
+                    "frac_of_sustained_peak": tf / pk["bf16_sustained"] if pk.get("bf16_sustained") else None,
                     "flops_per_launch": flops, "algorithmic_bytes_per_launch": bytes_, "avg_launch_ms": avg_ms,
                     "launches_timed": len(q_ms), "achieved_hbm_gbs": bytes_ / (avg_ms / 1e3) / 1e9,
                     "hbm_peak_gbs": pk["hbm"], "query_share_of_step": sum(q_ms) / sum(ms_steps),
                     "issued_mma_tflops": 3.0 * tf, "issued_mma_frac_of_peak": 3.0 * tf / pk["bf16"],
+                    "encoder": {"kernel": "conv_hx_kernel (+ stem / pool / upsample)", "bound": "tensor", "flops_per_image": ENC_FLOP,
+                                "avg_ms": avg_enc_ms, "achieved": ENC_FLOP / (avg_enc_ms / 1e3) / 1e12, "unit": "TFLOP/s",
+                                "frac": ENC_FLOP / (avg_enc_ms / 1e3) / 1e12 / pk["bf16"],
+                                "issued_mma_frac_of_peak": 3.0 * ENC_FLOP / (avg_enc_ms / 1e3) / 1e12 / pk["bf16"],
+                                "share_of_step": sum(enc_ms) / sum(ms_steps)},
                     "note": "fp32-faithful math: the MLP (600832 FLOP/point) bounds this kernel, not HBM "
                             "(arithmetic intensity ~4.3 kFLOP/B); `achieved`/`frac` count the ALGORITHMIC fp32 flops against "
                             "the measured dense bf16 tensor peak; the tensor cores execute 3 fp16 MMAs per algorithmic "
                             "MAC (hi*hi + lo*hi + hi*lo split), reported as issued_mma_*"}
-        try:
-            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                roofline["traffic"] = json.load(f).get(args.kernel_name)
-        except Exception:
-            pass
-        fit = fit_iteration_bench(net, str(dev)) if not args.no_fit else None
+        image20k = {"workload": "1x 5x512x512 image -> hourglass encoder -> 20000 query points, 4 heads (31 ch)",
+                    "value": world * 20000 / (ms20 / 1e3), "unit": "points/s", "ms_per_image": ms20,
+                    "e2e": {"value": world * 20000 / (ms20_e2e / 1e3), "unit": "points/s", "ms_per_image": ms20_e2e,
+                            "h2d_bytes_per_step": img_host.numel() * 4 + pts_host.numel() * 4, "d2h_bytes_per_step": out20_host.numel() * 4,
+                            "api": "CHORE.filter(pinned image) + CHORE.query(pinned points) + get_preds() -> pinned host (31 ch)"},
+                    "encoder_share": avg_enc_ms / ms20,
+                    "note": "the encoder dominates a 20k-point image (its roofline is roofline.encoder); the query of 20000 points is "
+                            "157 tiles of 128 on 148 SMs"}
         # CPU baseline: the oracle on a bounded sample of the same workload (rank 0, N = 1 only)
         cpu = None
         if world == 1 and not args.no_cpu:
@@ -315,27 +554,29 @@ def run_ours(args, rank, world, local_rank):
             torch.set_num_threads(cores)
             img = O.synth_images(0, B=1, size=512)
             start = RES[1] * RES[2] * (RES[0] // 2)
-            cpu_step(sd, img, cc.cpu(), args.cpu_points, start)          # warm-up (oneDNN primitive creation)
-            t0 = time.perf_counter()
+            cpu_sample(sd, img, cc.cpu(), args.cpu_points, start)          # warm-up (oneDNN primitive creation)
             reps = 2
-            for _ in range(reps):
-                cpu_step(sd, img, cc.cpu(), args.cpu_points, start)
-            dt = (time.perf_counter() - t0) / reps
-            cpu = {"value": args.cpu_points / dt, "unit": "points/s", "cores": cores, "kind": "port",
-                   "sample": f"encoder + {args.cpu_points} of {total} grid points per step (mid-volume slab), "
-                             f"torch CPU fp32, {torch.get_num_threads()} threads, {dt:.2f} s/step"}
+            parts = [cpu_sample(sd, img, cc.cpu(), args.cpu_points, start) for _ in range(reps)]
+            enc_s, q_s = sum(p[0] for p in parts) / reps, sum(p[1] for p in parts) / reps
+            comp = compose_cpu(enc_s, q_s, args.cpu_points)
+            cpu = {"value": comp["value"], "unit": "points/s", "cores": cores, "kind": "port",
+                   "encoder_s": enc_s, "query_points_per_s": comp["query_points_per_s"],
+                   "full_step_s_extrapolated": comp["full_step_s_extrapolated"],
+                   "sample": f"{reps} x [one encoder pass ({enc_s:.3f} s) + {args.cpu_points} of {total} grid points (mid-volume slab, "
+                             f"{q_s:.3f} s)], timed separately; value = {total} / (encoder_s + {total} / query_points_per_s); "
+                             f"torch CPU fp32, {torch.get_num_threads()} threads"}
+            image20k["cpu_baseline"] = cpu_image20k(sd, cc.cpu())
+            if fit is not None:
+                fit["cpu_baseline"] = cpu_fit_iteration(sd)
         line = {"metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "points_per_step_per_gpu": total, "chunk": CHUNK,
-                           "l2": "256 MiB flush between timed iterations (untimed); outputs 2.08 GB/step > L2",
-                           "weights": "seeded synthetic (unit gain), chore-release shapes",
-                           "parallelism": f"{world}x independent image+grid (weak), NCCL all-gather of summaries"},
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
                 "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": img_host.numel() * 4,
-                        "d2h_bytes_per_step": df_host.numel() * 4, "ms_per_step": e2e_ms.item() / args.steps,
-                        "api": "CHORE.filter(pinned image -> device) + Generator.eval_grid (4 heads) + df (2 ch) -> pinned host"},
+                        "d2h_bytes_per_step": df_host.numel() * 4, "ms_per_step": e2e_ms_per_step,
+                        "api": "CHORE.filter(pinned image -> device) + Generator.eval_grid_chunk (4 heads, 4 chunks) + df (2 of the 31 "
+                               "channels: what eval_grid's caller reads) -> pinned host, chunk k copied while chunk k+1 computes"},
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clk.summary(),
-                "fit": fit}
+                "image20k": image20k, "fit": fit, "strong": strong}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

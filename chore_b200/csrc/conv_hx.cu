@@ -453,8 +453,7 @@ __global__ void __launch_bounds__(kThreadsHx, 1) conv_hx_kernel(const HxParams p
 #pragma unroll
                     for (int i = 0; i < 8; ++i) __stcg(reinterpret_cast<float4 *>(mine + (size_t)(4 * i) * p.Ns + ci * 32), x[i]);
                 }
-                __threadfence();
-                __syncwarp();
+                __syncwarp();                               // the release below is cumulative over the warp's stores
                 if (lane == 0) {
                     asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p.part_cnt + tn) : "memory");
                     if (c_first < p.Ns) {                   // bounded wait: a lost arrival must not hang the GPU

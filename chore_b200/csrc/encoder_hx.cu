@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(256) upadd_stats_kernel(const float *__restric
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int xx = min(max(ix - 1 + k, 0), IW - 1);
-                const float4 v = __ldcg(lb + ((size_t)yy * IW + xx) * c4n);
+                const float4 v = __ldg(lb + ((size_t)yy * IW + xx) * c4n);   // taps are shared by neighbouring outputs: keep them in L1
                 rsum.x = fmaf(v.x, cx[k], rsum.x); rsum.y = fmaf(v.y, cx[k], rsum.y);
                 rsum.z = fmaf(v.z, cx[k], rsum.z); rsum.w = fmaf(v.w, cx[k], rsum.w);
             }

@@ -134,6 +134,16 @@ class Generator:
 
     # ---- model/sdf.py:4-48 semantics --------------------------------------------------------------
     @torch.no_grad()
+    def eval_grid_chunk(self, resolution: Sequence[int], crop_center: torch.Tensor, batch_index: int, start: int, count: int,
+                        outs, head_mask: int = _lib.HEAD_DF) -> None:
+        """One batch_eval chunk (model/sdf.py:30-41): grid points [start, start + count) of create_grid(resolution, pmin,
+        pmax) into the preallocated per-head (n_out, X*Y*Z) tensors `outs` -- lets a caller overlap the copy of one chunk
+        with the evaluation of the next."""
+        feat, skip = self.model._maps()
+        cc = crop_center.detach().to(feat.device, torch.float32).contiguous()
+        self.model.handle.query_grid(feat, skip, cc, batch_index, resolution, self.pmin, self.pmax, start, count, head_mask, outs)
+
+    @torch.no_grad()
     def eval_grid(self, resolution: Sequence[int], crop_center: torch.Tensor, batch_index: int = 0,
                   head_mask: int = _lib.HEAD_DF, chunk: int = 1 << 22):
         """Field on create_grid(resolution, pmin, pmax): per-head (n_out, X, Y, Z) tensors."""
