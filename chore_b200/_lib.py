@@ -48,7 +48,7 @@ SIGNATURES = {
     "chore_query_bwd": (_I, [_P, _P, _P, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "chore_query_bwd_workspace_bytes": (C.c_size_t, [_I, _I]),
     "chore_query_bwd_ws": (_I, [_P, _P, _P, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
-    "chore_query_grid": (_I, [_P, _P, _P, _I, _I, _P, _I, C.POINTER(_I), C.POINTER(C.c_float), C.POINTER(C.c_float),
+    "chore_query_grid": (_I, [_P, _P, _P, _I, _I, _P, _I, C.POINTER(_I), C.POINTER(C.c_double), C.POINTER(C.c_double),
                               _I64, _I64, _U32, _P, _P, _P, _P, _P]),
     "chore_lbs_load_model": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I]),
     "chore_lbs_fwd": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P]),
@@ -211,8 +211,8 @@ class Handle:
         """outs: per-head (nout, total) tensors of image b (or None); fills columns [start, start+count)."""
         check_cuda(feat, skip, crop_center, *outs)
         res_c = (_I * 3)(*[int(r) for r in res])
-        mn = (C.c_float * 3)(*[float(x) for x in b_min])
-        mx = (C.c_float * 3)(*[float(x) for x in b_max])
+        mn = (C.c_double * 3)(*[float(x) for x in b_min])      # float64 like create_grid's numpy arithmetic
+        mx = (C.c_double * 3)(*[float(x) for x in b_max])
         with torch.cuda.device(self.device):
             self._check(self.lib.chore_query_grid(self.h, feat.data_ptr(), skip.data_ptr(), feat.shape[1], feat.shape[2],
                                                   crop_center.data_ptr(), b, res_c, mn, mx, start, count, head_mask,

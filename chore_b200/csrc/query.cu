@@ -666,8 +666,8 @@ extern "C" int chore_query_fwd(chore_handle *h, const float *feat, const float *
 }
 
 extern "C" int chore_query_grid(chore_handle *h, const float *feat, const float *skip, int fh, int fw,
-                                const float *crop_center, int b, const int res[3], const float b_min[3],
-                                const float b_max[3], int64_t start, int64_t count, uint32_t head_mask,
+                                const float *crop_center, int b, const int res[3], const double b_min[3],
+                                const double b_max[3], int64_t start, int64_t count, uint32_t head_mask,
                                 float *df, float *pca, float *parts, float *centers, void *stream) {
     if (int rc = check_maps(h, feat, skip, fh, fw)) return rc;
     CHORE_CHECK(crop_center && res && b_min && b_max && b >= 0, "bad grid arguments");
@@ -687,8 +687,8 @@ extern "C" int chore_query_grid(chore_handle *h, const float *feat, const float 
     q.B = 1; q.N = total; q.n_start = start; q.n_count = count;
     q.grid_mode = 1; q.ry = res[1]; q.rz = res[2]; q.batch_index = b;
     for (int i = 0; i < 3; ++i) {
-        q.step[i] = ((double)b_max[i] - (double)b_min[i]) / (double)res[i];
-        q.bmin[i] = (double)b_min[i];
+        q.step[i] = (b_max[i] - b_min[i]) / (double)res[i];
+        q.bmin[i] = b_min[i];
     }
     q.head_mask = head_mask;
     // outputs are (nout, total) rows of image b; the kernel indexes them with b = batch_index,

@@ -44,7 +44,7 @@ int chore_ws2_reserve(chore_handle *h, size_t bytes) { return reserve(&h->ws2, &
 int chore_lbs_ws_reserve(chore_handle *h, size_t bytes) { return reserve(&h->lbs_ws, &h->lbs_ws_bytes, bytes); }
 
 extern "C" const char *chore_last_error(void) { return g_err; }
-extern "C" int chore_abi_version(void) { return 2; }
+extern "C" int chore_abi_version(void) { return 3; }
 extern "C" uint64_t chore_launch_count(void) { return g_launch_count.load(); }
 
 extern "C" int chore_create(int device, chore_handle **out) {

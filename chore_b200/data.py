@@ -101,8 +101,12 @@ def write_ply(path: str, verts: np.ndarray, faces: Optional[np.ndarray] = None) 
 # landmark regressor on mocap vertices (lib_smpl/body_landmark.py:16-28,61-65)
 # ---------------------------------------------------------------------------------------------
 class BodyLandmarks:
-    def __init__(self, assets_root: str):
-        self.body25_reg = pkl.load(open(join(assets_root, "body25_regressor.pkl"), "rb"), encoding="latin1").T
+    def __init__(self, assets_root: Optional[str] = None, body25_reg=None):
+        """assets_root: directory with body25_regressor.pkl (the reference's assets/); or pass the (25, 6890) sparse
+        regressor directly."""
+        if body25_reg is None:
+            body25_reg = pkl.load(open(join(assets_root, "body25_regressor.pkl"), "rb"), encoding="latin1").T
+        self.body25_reg = body25_reg
 
     def get_body_kpts(self, verts: np.ndarray) -> np.ndarray:
         """(6890,3) SMPL vertices -> (25,3) body joints."""
@@ -166,7 +170,8 @@ class TestData:
     __test__ = False          # not a pytest class
 
     def __init__(self, data_paths, batch_size=1, num_workers=0, dtype=np.float32, image_size=(512, 512), input_type="RGBM3",
-                 crop_size=1200, use_mean_center=False, assets_root: Optional[str] = None, write_crop_info: bool = True, **kwargs):
+                 crop_size=1200, use_mean_center=False, assets_root: Optional[str] = None, write_crop_info: bool = True,
+                 body25_reg=None, **kwargs):
         assert input_type == "RGBM3"
         self.data_paths, self.batch_size, self.num_workers, self.dtype = list(data_paths), batch_size, num_workers, dtype
         self.img_size = tuple(image_size)                                 # width, height
@@ -174,7 +179,7 @@ class TestData:
         self.mean_crop_center = np.array([1008.0, 995.0])                 # BEHAVE training-set mean (test_data.py:32)
         self.use_mean_center = use_mean_center
         self.depth = kwargs.get("z_0", 2.2)
-        self.landmark = BodyLandmarks(assets_root) if assets_root is not None else None
+        self.landmark = BodyLandmarks(assets_root, body25_reg) if (assets_root is not None or body25_reg is not None) else None
         self.write_crop_info = write_crop_info
         self.aug_blur = 0.0
 

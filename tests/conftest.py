@@ -50,3 +50,27 @@ def golden_smpl_assets(g):
             for i, L in enumerate((25, 70, 42))]
     pri = {k[len("prior_"):]: g[k] for k in g if k.startswith("prior_")}
     return regs, pri
+
+
+def pure_rel_err(a, b, floor_frac=0.05):
+    """max |a-b| / |b| over the elements with |b| > floor_frac * rms(b): the plain relative error north_star quotes,
+    without rel_err's rms term in the denominator (elements near zero are excluded instead)."""
+    import torch
+    a = torch.as_tensor(a).double().cpu()
+    b = torch.as_tensor(b).double().cpu()
+    keep = b.abs() > floor_frac * b.pow(2).mean().sqrt()
+    return ((a - b).abs()[keep] / b.abs()[keep]).max().item() if bool(keep.any()) else 0.0
+
+
+_REPORT = os.path.join(ROOT, "gpurun_out", "parity_report.jsonl")
+
+
+def report(test, **values):
+    """Append measured errors to gpurun_out/parity_report.jsonl (scratch; read after a GPU run)."""
+    import json
+    try:
+        os.makedirs(os.path.dirname(_REPORT), exist_ok=True)
+        with open(_REPORT, "a") as f:
+            f.write(json.dumps({"test": test, **{k: float(v) for k, v in values.items()}}) + "\n")
+    except OSError:
+        pass

@@ -36,7 +36,7 @@ def test_binding_covers_header(lib_path):
     from chore_b200 import _lib
     assert sorted(_lib.SIGNATURES) == declared_symbols()
     lib = _lib.load_library()
-    assert lib.chore_abi_version() == 2
+    assert lib.chore_abi_version() == 3
     assert lib.chore_launch_count() >= 0
 
 

@@ -10,11 +10,13 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import load_golden, rel_err
+from conftest import load_golden, pure_rel_err, rel_err, report
 from oracle import chore_oracle as O
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
+ENC_TOL = 1e-4      # encoder output after ~60 GroupNorm + conv layers: measured 1.1e-5 .. 3.4e-5 (gpurun_out/parity_report.jsonl)
+E2E_TOL = 1e-4      # encoder + query end to end: measured <= 3.2e-5
 DEV = "cuda:0"
 
 
@@ -211,9 +213,11 @@ def test_encoder_vs_golden_128(net):
     net.filter(img)
     feat, tmpx, normx = net.get_im_feat(), net.tmpx, net.normx
     assert feat.shape == (2, 256, 32, 32) and tmpx.shape == (2, 64, 64, 64)
+    report("encoder_128", tmpx=rel_err(tmpx, g["tmpx"]), normx=rel_err(normx[:, :, ::4, ::4], g["normx"]), feat=rel_err(feat, g["feat"]),
+           feat_pure=pure_rel_err(feat, g["feat"]))
     assert rel_err(tmpx, g["tmpx"]) < TOL, rel_err(tmpx, g["tmpx"])
     assert rel_err(normx[:, :, ::4, ::4], g["normx"]) < TOL, rel_err(normx[:, :, ::4, ::4], g["normx"])
-    assert rel_err(feat, g["feat"]) < 5e-4, rel_err(feat, g["feat"])     # ~60 GN+conv layers deep
+    assert rel_err(feat, g["feat"]) < ENC_TOL, rel_err(feat, g["feat"])     # ~60 GN+conv layers deep
 
 
 def test_encoder_vs_golden_512(net):
@@ -222,8 +226,10 @@ def test_encoder_vs_golden_512(net):
     net.filter(img)
     feat, tmpx = net.get_im_feat(), net.tmpx
     assert feat.shape == (1, 256, 128, 128) and tmpx.shape == (1, 64, 256, 256)
+    report("encoder_512", tmpx=rel_err(tmpx[:, :, ::8, ::8], g["tmpx_s8"]), feat=rel_err(feat[:, :, ::8, ::8], g["feat_s8"]),
+           feat_pure=pure_rel_err(feat[:, :, ::8, ::8], g["feat_s8"]))
     assert rel_err(tmpx[:, :, ::8, ::8], g["tmpx_s8"]) < TOL
-    assert rel_err(feat[:, :, ::8, ::8], g["feat_s8"]) < 5e-4, rel_err(feat[:, :, ::8, ::8], g["feat_s8"])
+    assert rel_err(feat[:, :, ::8, ::8], g["feat_s8"]) < ENC_TOL, rel_err(feat[:, :, ::8, ::8], g["feat_s8"])
     from oracle.make_golden import checksum
     ck = checksum(feat.cpu().contiguous())
     assert abs(ck[0] - g["feat_ck"][0]) < 1e-3 * abs(g["feat_ck"][2]) * feat.numel() ** 0.5
@@ -235,8 +241,9 @@ def test_encoder_refinit_weights():
     n = chore_b200.CHORE(device=DEV)
     n.load_state_dict(O.make_state_dict(int(g["weights_seed"]), "ref_init"))
     n.filter(O.synth_images(int(g["seed"]), B=1, size=128).to(DEV))
+    report("encoder_refinit", tmpx=rel_err(n.tmpx, g["tmpx"]), feat=rel_err(n.get_im_feat(), g["feat"]))
     assert rel_err(n.tmpx, g["tmpx"]) < TOL
-    assert rel_err(n.get_im_feat(), g["feat"]) < 5e-4
+    assert rel_err(n.get_im_feat(), g["feat"]) < ENC_TOL
 
 
 def test_encode_then_query_end_to_end(net, sd):
@@ -250,8 +257,87 @@ def test_encode_then_query_end_to_end(net, sd):
     with torch.no_grad():
         ref = O.query(sd, f, t, pts, cc)
     net.query(pts.to(DEV), crop_center=cc.to(DEV))
-    for got, want in zip(net.get_preds(), ref[:4]):
-        assert rel_err(got, want) < 1e-3
+    errs = [rel_err(got, want) for got, want in zip(net.get_preds(), ref[:4])]
+    report("encode_then_query", df=errs[0], pca=errs[1], parts=errs[2], centers=errs[3])
+    for e in errs:
+        assert e < E2E_TOL, errs
+
+
+def test_query_grid_256_planes_vs_golden(net):
+    """BASELINE config 2 at its real size: three x-planes (3 x 65 536 points) of the 256^3 grid, coordinates generated in the
+    kernel, against the reference's create_grid (model/sdf.py:4-27) + CHORE.query run."""
+    g = load_golden("query_grid256.npz")
+    feat, tmpx = O.synth_features(int(g["seed"]), B=1)
+    set_maps(net, feat, tmpx)
+    res = [int(r) for r in g["res"]]
+    total, plane = res[0] * res[1] * res[2], res[1] * res[2]
+    outs = [torch.empty(c, total, device=DEV) for c in (2, 9, 14, 6)]
+    cc = T(g["crop_center"])
+    for ix in g["planes"]:
+        net.handle.query_grid(*net._maps(), cc, 0, res, list(g["bmin"]), list(g["bmax"]), int(ix) * plane, plane, 15, outs)
+    sel = torch.cat([torch.arange(int(ix) * plane, (int(ix) + 1) * plane) for ix in g["planes"]]).to(DEV)
+    df, pca, parts, centers = [o[:, sel] for o in outs]
+    st = int(g["stride"])
+    errs = {"df": rel_err(df, g["df"][0]), "pca": rel_err(pca[:, ::st], g["pca_s"].reshape(9, -1)),
+            "parts": rel_err(parts[:, ::st], g["parts_s"][0]), "centers": rel_err(centers[:, ::st], g["centers_s"][0])}
+    inimg = (torch.from_numpy(g["df"][0][0]) != O.OUT_DIST)[::st]
+    pe = ((parts[:, ::st].cpu().double() - torch.from_numpy(g["parts_s"][0]).double()).abs().amax(0))
+    scale = torch.from_numpy(g["parts_s"][0]).double().pow(2).mean().sqrt()
+    report("grid256_planes", **errs, df_pure=pure_rel_err(df, g["df"][0]), parts_abs_err_in_image=float(pe[inimg].max() / scale),
+           parts_abs_err_out_of_image=float(pe[~inimg].max() / scale), frac_in_image=float(inimg.float().mean()),
+           parts_rms=float(scale), parts_absmax=float(torch.from_numpy(g["parts_s"][0]).abs().max()))
+    for k, e in errs.items():
+        assert e < TOL, (k, e)
+    # OUT_DIST mask and part labels: bit-exact where the reference's top-2 margin is clear
+    assert torch.equal(df.cpu() == O.OUT_DIST, torch.from_numpy(g["df"][0]) == O.OUT_DIST)
+    clear = torch.from_numpy(g["top2_margin"][0].astype(np.float32)) > 5e-4
+    same = parts.argmax(0).cpu() == torch.from_numpy(g["parts_argmax"][0]).long()
+    assert bool(same[clear].all()), int((~same & clear).sum())
+
+
+def test_query_batch32_vs_golden(net):
+    """BASELINE config 4 batch shape: 32 images x 1 024 points in one launch, per-image crop centres."""
+    g = load_golden("query_b32.npz")
+    B, N = 32, 1024
+    feat, tmpx = O.synth_features(int(g["seed"]), B=B, hw=64)
+    set_maps(net, feat, tmpx)
+    cc = torch.from_numpy(g["crop_center"])
+    pts = torch.cat([O.synth_points("init_box", 97, B, N // 2), O.synth_points("frustum", 98, B, N // 2, cc)], 1)
+    from oracle.make_golden import checksum
+    assert np.allclose(checksum(pts), g["points_ck"], rtol=1e-6)
+    outs, _ = net.handle.query_fwd(*net._maps(), pts.to(DEV), cc.to(DEV), 15)
+    df, pca, parts, centers = outs
+    st = int(g["stride"])
+    errs = {"df": rel_err(df, g["df"]), "pca": rel_err(pca[..., ::st], g["pca_s"].reshape(B, 9, -1)),
+            "parts": rel_err(parts[..., ::st], g["parts_s"]), "centers": rel_err(centers[..., ::st], g["centers_s"])}
+    report("query_b32", **errs)
+    for k, e in errs.items():
+        assert e < TOL, (k, e)
+    assert (parts.argmax(1).cpu() != torch.from_numpy(g["parts_argmax"]).long()).float().mean() < 1e-3
+
+
+def test_example_frame_end_to_end_vs_golden(net):
+    """The reference's shipped demo frame (tests/golden/example_frame = example/000000117377): TestData crop -> CHORE.filter ->
+    CHORE.query against the reference's own TestData + network run -- realistic (non white-noise) input."""
+    import os
+    import chore_b200
+    from conftest import GOLDEN, golden_smpl_assets
+    g = load_golden("example_frame.npz")
+    regs, _ = golden_smpl_assets(load_golden("fit_smpl_full.npz"))
+    ds = chore_b200.TestData([os.path.join(GOLDEN, "example_frame", "k1.color.jpg")], image_size=(512, 512), crop_size=1200,
+                             body25_reg=regs[0], write_crop_info=False)
+    item = ds.get_item(0)
+    assert np.array_equal(item["images"][:, ::4, ::4], g["images_own_s4"])
+    net.filter(torch.from_numpy(item["images"]).unsqueeze(0).to(DEV))
+    feat, tmpx = net.get_im_feat(), net.tmpx
+    e_feat, e_tmpx = rel_err(feat[:, :, ::8, ::8], g["feat_s8"]), rel_err(tmpx[:, :, ::8, ::8], g["tmpx_s8"])
+    cc = torch.from_numpy(item["crop_center"]).float().unsqueeze(0).to(DEV)
+    net.query(T(g["points"]), crop_center=cc)
+    errs = {k: rel_err(got, g[k]) for k, got in zip(("df", "pca", "parts", "centers"), net.get_preds())}
+    report("example_frame", feat=e_feat, tmpx=e_tmpx, feat_pure=pure_rel_err(feat[:, :, ::8, ::8], g["feat_s8"]), **errs)
+    assert e_tmpx < TOL and e_feat < ENC_TOL, (e_feat, e_tmpx)
+    for k, e in errs.items():
+        assert e < E2E_TOL, (k, e)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -524,12 +610,12 @@ def test_fused_fit_loop_matches_reference_loop_semantics(net, smpl_layer):
             fit.sum_dict(fit.forward_smpl(sa, data, "kpts"), wd, it / 3).backward(); opt_s.step()
             fit.sum_dict(fit.forward_step(net, sa, data, Ra, ta, sca, "object only", noise=noise), wd, it / 3).backward(); opt_o.step()
 
-    def run(graphed, lr):
+    def run(graphed, lr, outer=outer_iters, inner=inner):
         sf = fit.split_smpl(w); Rf, tf, scf = mkobj()
         fused = chore_b200.FusedFitSteps(net, sf, data, Rf, tf, scf, lr_smpl=lr, lr_obj=lr, fitter=fit, phase="kpts")
         s_step = fused.graphed()[0] if graphed else fused.smpl_step
         o_step = lambda: fused.object_step(noise)      # (a captured object step draws its own noise: keep it pinned)
-        for it in outer_iters:
+        for it in outer:
             fused.zero_grad(); fused.set_decay(it / 3)
             for _ in range(inner):
                 s_step(); o_step()
@@ -543,13 +629,15 @@ def test_fused_fit_loop_matches_reference_loop_semantics(net, smpl_layer):
             assert rel_err(a.grad, b.grad) < 2e-4, (graphed, n, rel_err(a.grad, b.grad))
         # the capture's warm-up steps were undone: exactly 6 updates were applied
         assert int(fused.opt_smpl.step_count) == len(outer_iters) * inner and int(fused.opt_obj.step_count) == len(outer_iters) * inner
-    # (2) learning rate 0.006: replaying the captured step gives bit-for-bit the eager trajectory (same kernels, same order),
-    #     i.e. the warm-up left nothing behind in parameters, moments or accumulators
-    _, se, _ = run(False, 0.006)
-    _, sg2, _ = run(True, 0.006)
+    # (2) learning rate 0.006, ONE step: the replayed step lands where the eager step lands, i.e. the warm-up left nothing behind in
+    #     parameters, moments or accumulators (3 stray updates would show as ~0.02).  Only one step is compared: the adjoint kernels
+    #     use fp32 atomics, and on white-noise features the Adam trajectory amplifies that 5e-10 run-to-run noise by ~30x per step
+    #     (measured: two EAGER runs of the same 6 steps differ by 2e-3).
+    _, se, _ = run(False, 0.006, outer=(3,), inner=1)
+    _, sg2, _ = run(True, 0.006, outer=(3,), inner=1)
     for n in names:
-        assert torch.equal(getattr(se, n), getattr(sg2, n)), n
-        assert not torch.equal(getattr(se, n), getattr(sa, n)), n        # ... and the parameters did move
+        assert (getattr(se, n) - getattr(sg2, n)).abs().max() < 1e-6, n
+        assert (getattr(se, n) - getattr(sa, n)).abs().max() > 1e-3, n        # ... and the parameters did move (one Adam step = lr)
     # the 'global' phase of optimize_smpl: only top_betas and trans move, lr 0.02
     sg = fit.split_smpl(w); Rg, tg, scg = mkobj()
     fused = chore_b200.FusedFitSteps(net, sg, data, Rg, tg, scg, fitter=fit, phase="global")
