@@ -64,6 +64,10 @@ SIGNATURES = {
     "chore_add_rowvec": (_I, [_P, _P, _P, _I, _I, _F, _P]),
     "chore_surface_clamp_grad": (_I, [_P, _P, _I, _F, _I, _I, _P, _P]),
     "chore_surface_step": (_I, [_P, _P, _P, _P, _I, _F, _I, _I, _P, _P]),
+    "chore_gen_compact": (_I, [_P, _P, _I, _F, _F, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "chore_gen_resample": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _F, C.c_uint64, C.c_uint64, _P, _P, _P, _P]),
+    "chore_gen_total": (_I, [_P, _P, _I, _P, _P]),
+    "chore_gen_finalize": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P]),
     "chore_adam_step": (_I, [_P, C.POINTER(AdamEntry), _I, _F, _F, _F, _F, _P, _P, _P, _P]),
     "chore_rigid_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P]),
     "chore_rigid_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
@@ -352,6 +356,41 @@ class Handle:
             self._check(self.lib.chore_surface_step(self.h, points.data_ptr(), g_points.data_ptr(), df.data_ptr(), df_idx, threshold,
                                                     points.shape[0], points.shape[1], out.data_ptr(), _stream()))
         return out
+
+    # ---- generator bookkeeping (csrc/generator.cu) --------------------------------------------------
+    def gen_compact(self, df, df_idx, threshold, filter_val, samples, packed, iter_count, surf=None, preds=None, out=None) -> None:
+        """out = (points (B,cap,3), labels int32 (B,cap), pca (B,cap,9), centers (B,cap,6), count int32 (B,)) or None."""
+        B, N = samples.shape[0], samples.shape[1]
+        append = out is not None
+        cap = out[0].shape[1] if append else 0
+        pca, parts, centers = preds if append else (None, None, None)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.chore_gen_compact(self.h, df.data_ptr(), df_idx, threshold, filter_val, _ptr(surf), samples.data_ptr(),
+                                                   _ptr(pca), _ptr(parts), _ptr(centers), B, N, cap, int(append),
+                                                   *([_ptr(o) for o in out] if append else [None] * 5), packed.data_ptr(),
+                                                   iter_count.data_ptr(), _stream()))
+
+    def gen_resample(self, packed, iter_count, samples_init, sample_num, sigma_hit, sigma_miss, seed, offset, uniforms=None,
+                     normals=None):
+        B, N = packed.shape[0], packed.shape[1]
+        out = torch.empty(B, sample_num, 3, device=packed.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.chore_gen_resample(self.h, packed.data_ptr(), iter_count.data_ptr(), samples_init.data_ptr(), B, N,
+                                                    samples_init.shape[1], sample_num, sigma_hit, sigma_miss, seed, offset,
+                                                    _ptr(uniforms), _ptr(normals), out.data_ptr(), _stream()))
+        return out
+
+    def gen_total(self, iter_count, samples_count) -> None:
+        with torch.cuda.device(self.device):
+            self._check(self.lib.chore_gen_total(self.h, iter_count.data_ptr(), iter_count.shape[0], samples_count.data_ptr(), _stream()))
+
+    def gen_finalize(self, out_pca, out_centers, samples_count):
+        B, cap = out_pca.shape[0], out_pca.shape[1]
+        pca_mean, cen_mean = torch.empty(B, 9, device=out_pca.device), torch.empty(B, 6, device=out_pca.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.chore_gen_finalize(self.h, out_pca.data_ptr(), out_centers.data_ptr(), B, cap, samples_count.data_ptr(),
+                                                    pca_mean.data_ptr(), cen_mean.data_ptr(), _stream()))
+        return pca_mean, cen_mean
 
     def adam_step(self, entries, n: int, lr: float, beta1: float, beta2: float, eps: float, step, gscale=None, loss=None) -> None:
         with torch.cuda.device(self.device):

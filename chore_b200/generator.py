@@ -3,6 +3,9 @@
 and the dense-grid evaluation of model/sdf.py:4-48 (create_grid / eval_grid)."""
 from __future__ import annotations
 
+import os
+from glob import glob
+from os.path import isfile
 from typing import Dict, Sequence
 
 import numpy as np
@@ -14,18 +17,95 @@ from .net import heads
 
 
 class Generator:
-    def __init__(self, model, threshold: float = 2.0, filter_val: float = 0.004, sparse_thres: float = 0.03,
-                 device="cuda:0", fused: bool = True):
-        """fused: run approx_surface through the autograd-free kernel sequence when the model is a chore_b200.CHORE
-        (same values up to the last bit of F.normalize's norm); False keeps the reference's autograd formulation."""
-        self.fused = fused
-        self.model = model
-        self.threshold = threshold
-        self.filter_val = filter_val
+    """Drop-in for recon/generator.py:Generator (same constructor arguments, defaults, methods and result dict).
+
+    Extensions, all keyword-only:
+      fused      approx_surface as the autograd-free kernel sequence (same values up to the last bit of F.normalize's norm);
+                 False keeps the reference's autograd formulation on the same kernels.
+      rng        "reference": gen_pc_batch draws indices / noise from torch's CPU generator in the reference's order (bit-exact
+                 against the reference loop, tests/test_generator_cpu.py) and keeps its per-image Python bookkeeping;
+                 "device": the whole loop stays on the GPU (csrc/generator.cu: ordered stream compaction, Philox resampling,
+                 min-count and final reductions), ONE host sync per outer iteration (the loop condition).  Seed contract:
+                 Philox4x32-10, seed = `seed`, subsequence = image * sample_num + sample, offset = outer iteration.
+      experiments_root   where experiments/<exp_name>/checkpoints lives (the reference derives it from its own file location).
+    exp_name=None skips checkpoint discovery (weights already loaded into `model`)."""
+
+    def __init__(self, model, exp_name=None, threshold=1.0, checkpoint=None, device="cuda", multi_gpus=True, sparse_thres=0.05,
+                 filter_val=0.03, *, fused: bool = True, rng: str = "reference", seed: int = 0, experiments_root=None):
+        assert rng in ("reference", "device")
+        self.fused, self.rng, self.seed = fused, rng, int(seed)
         self.sparse_thres = sparse_thres
-        self.device = device
+        self.filter_val = filter_val
+        self.sample_num = 100000
+        self.device = torch.device(device) if not isinstance(device, torch.device) else device
+        self.model = model.to(self.device) if hasattr(model, "to") else model
+        if hasattr(self.model, "eval"):
+            self.model.eval()
+        self.threshold = threshold
+        self.multi_gpus = multi_gpus
+        if exp_name is not None:
+            root = experiments_root or os.path.join(os.getcwd(), "experiments")
+            self.exp_path = os.path.join(root, exp_name) + os.sep
+            self.checkpoint_path = os.path.join(self.exp_path, "checkpoints") + os.sep
+            assert os.path.exists(self.checkpoint_path), f"{self.checkpoint_path} does not exist!"
+            self.load_checkpoint(checkpoint)
+        if hasattr(self.model, "parameters"):
+            for param in self.model.parameters():
+                param.requires_grad = False
         self.pmin = np.array([-3.0, -0.9, 0.2])      # recon/generator.py:45-48
         self.pmax = np.array([3.0, 1.8, 4.0])
+
+    # ---- checkpoints (recon/generator.py:219-267) ------------------------------------------------------
+    def get_val_min_ck(self):
+        files = glob(self.exp_path + "val_min=*")
+        if len(files) == 0:
+            return None
+        log = np.load(files[0])
+        return log[2] if isfile(self.checkpoint_path + str(log[2])) else None
+
+    def find_best_checkpoint(self, checkpoints):
+        """val_min=<epoch>.npy names the best checkpoint; otherwise the latest `checkpoint_{h}h:{m}m:{s}s_{secs}.tar`."""
+        best = self.get_val_min_ck()
+        if best is not None:
+            return self.checkpoint_path + best
+        secs = np.sort(np.array([os.path.splitext(os.path.basename(p))[0].split("_")[-1] for p in checkpoints], dtype=float))[-1]
+        h, m, sec = int(secs / 3600), int((secs / 60) % 60), int(secs % 60)
+        return self.checkpoint_path + "checkpoint_{}h:{}m:{}s_{}.tar".format(h, m, sec, secs)
+
+    def load_checkpoint(self, checkpoint):
+        if checkpoint is None:
+            checkpoints = glob(self.checkpoint_path + "/*")
+            if len(checkpoints) == 0:
+                print("No checkpoints found at {}".format(self.checkpoint_path))
+                return 0, 0
+            path = self.find_best_checkpoint(checkpoints)
+        else:
+            path = self.checkpoint_path + "{}".format(checkpoint)
+        ck = torch.load(path, map_location="cpu", weights_only=False)
+        print("Loaded checkpoint from: {}".format(path))
+        sd = ck["model_state_dict"]
+        if self.multi_gpus:                          # DistributedDataParallel prefix
+            sd = {k.replace("module.", ""): v for k, v in sd.items()}
+        self.model.load_state_dict(sd)
+        return ck["epoch"], ck["training_time"]
+
+    # ---- small pieces of the reference interface -----------------------------------------------------------
+    def prep_query_input(self, batch):
+        return {"crop_center": batch.get("crop_center").to(self.device)}
+
+    def filter(self, data):
+        "encode image features"
+        self.model.filter(data["images"].to(self.device))
+
+    def get_grid_samples(self, sample_num, batch_size=1):
+        return self.init_samples(sample_num, batch_size)
+
+    def generate_pclouds_batch(self, data, num_steps=10, num_points=50000, mute=False):
+        """recon/generator.py:102-121: encode, then the neural point clouds of the human and the object field."""
+        self.filter(data)
+        batch_size = data.get("images").shape[0]
+        samples = self.get_grid_samples(30000, batch_size=batch_size)
+        return {t: self.gen_pc_batch(self.model, t, samples, num_points, data, num_steps, mute=mute) for t in ("human", "object")}
 
     # ---- recon/generator.py:50-79 ---------------------------------------------------------------
     def approx_surface(self, model, samples, num_steps, query_input, df_type):
@@ -82,8 +162,12 @@ class Generator:
         return samples
 
     # ---- recon/generator.py:123-217 -------------------------------------------------------------
-    def gen_pc_batch(self, model, df_type, samples_init, num_points, query_input, num_steps=10, max_iter=100,
+    def gen_pc_batch(self, model, df_type, samples_init, num_points, batch, num_steps=10, max_iter=100, mute=False,
                      sample_num=20000) -> Dict[str, torch.Tensor]:
+        """recon/generator.py:123-188.  `batch`: the loader batch (or any dict with 'crop_center')."""
+        query_input = self.prep_query_input(batch)
+        if self.rng == "device" and hasattr(model, "handle") and self.device.type == "cuda":
+            return self._gen_pc_batch_device(model, df_type, samples_init, num_points, query_input, num_steps, max_iter, sample_num)
         df_idx = 0 if df_type == "human" else 1
         B = samples_init.shape[0]
         names = ["points", "pca_axis", "parts", "centers"]
@@ -99,10 +183,10 @@ class Generator:
                 counts = []
                 for i in range(B):
                     m = mask[i]
-                    out["points"][i].append(surf[i, m].detach())
-                    out["pca_axis"][i].append(preds[1][i][..., m].detach())
-                    out["parts"][i].append(preds[2][i][:, m].detach())
-                    out["centers"][i].append(preds[3][i][:, m].detach())
+                    out["points"][i].append(surf[i, m].detach().cpu())            # parse_preds (:88-100) collects on the host
+                    out["pca_axis"][i].append(preds[1][i][..., m].detach().cpu())
+                    out["parts"][i].append(preds[2][i][:, m].detach().cpu())
+                    out["centers"][i].append(preds[3][i][:, m].detach().cpu())
                     counts.append(int(m.sum()))
                 count += min(counts)
             new = []
@@ -131,6 +215,43 @@ class Generator:
                 comb.append(torch.argmax(o, 0) if n == "parts" else torch.mean(o, -1))
             res[n] = torch.stack(comb, 0)
         return res
+
+    @torch.no_grad()
+    def _gen_pc_batch_device(self, model, df_type, samples_init, num_points, query_input, num_steps, max_iter, sample_num,
+                             randoms=None):
+        """gen_pc_batch with every stage on the GPU.  `randoms`: optional callable (it, iter_count) -> (uniforms (B,sample_num),
+        normals (B,sample_num,3)) replacing the Philox draws (tests replay the reference's CPU draws through it)."""
+        h = model.handle
+        df_idx = 0 if df_type == "human" else 1
+        dev = self.device
+        init = samples_init.detach().to(dev, torch.float32).contiguous()
+        B, n_init = init.shape[0], init.shape[1]
+        cap = int(num_points) + max(n_init, sample_num)
+        out = (torch.empty(B, cap, 3, device=dev), torch.empty(B, cap, dtype=torch.int32, device=dev),
+               torch.empty(B, cap, 9, device=dev), torch.empty(B, cap, 6, device=dev), torch.zeros(B, dtype=torch.int32, device=dev))
+        iter_count = torch.zeros(B, dtype=torch.int32, device=dev)
+        total = torch.zeros(1, dtype=torch.int32, device=dev)
+        samples, it, count = init, 0, 0
+        while count < num_points:
+            surf, preds = self.approx_surface(model, samples, num_steps, query_input, df_type)
+            n = samples.shape[1]
+            packed = torch.empty(B, n, 3, device=dev)
+            append = it > 0
+            h.gen_compact(preds[0], df_idx, float(self.threshold), float(self.filter_val), samples.detach().contiguous(), packed, iter_count,
+                          surf=surf.detach().contiguous(), preds=(preds[1].reshape(B, 9, -1), preds[2], preds[3]) if append else None,
+                          out=out if append else None)
+            if append:
+                h.gen_total(iter_count, total)
+            u, nrm = randoms(it, iter_count) if randoms is not None else (None, None)
+            samples = h.gen_resample(packed, iter_count, init, sample_num, float(self.threshold) / 3, 0.5, self.seed + (df_idx << 32), it, u, nrm)
+            if append:
+                count = int(total.item())            # the only host sync of the outer iteration: the loop condition
+            it += 1
+            if it == max_iter:
+                raise RuntimeError("point generation failed after 100 iterations")
+        pca_mean, cen_mean = h.gen_finalize(out[2], out[3], total)
+        return {"points": out[0][:, :count].clone(), "pca_axis": pca_mean.view(B, 3, 3), "parts": out[1][:, :count].long(),
+                "centers": cen_mean}
 
     # ---- model/sdf.py:4-48 semantics --------------------------------------------------------------
     @torch.no_grad()

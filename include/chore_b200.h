@@ -223,6 +223,30 @@ int chore_surface_clamp_grad(chore_handle *h, const float *df, int df_idx, float
 int chore_surface_step(chore_handle *h, const float *points, const float *g_points, const float *df, int df_idx,
                        float threshold, int B, int N, float *out_points, void *stream);
 
+/* ---- bookkeeping of Generator.gen_pc_batch (recon/generator.py:123-217) on the device: what the reference does with
+ *      boolean indexing, Python lists and .cpu() / .item() round trips per image and outer iteration.  B images, N samples
+ *      of this outer iteration; `cap` = capacity of the per-image output buffers. -------------------------------------- */
+/* hit = min(df[:, df_idx], threshold) < filter_val.  STABLE (index-order) compaction per image: the pre-projection
+ * `samples` of the hits are packed into `packed` (B,N,3) and `iter_count[b]` = number of hits; with append != 0 the
+ * projected points `surf`, the part label (argmax of the 14 logits, first maximum), the 9 PCA values and the 6 centre
+ * values of the hits are appended at out_count[b] (entries beyond cap are dropped) -- parse_preds (:88-100). */
+int chore_gen_compact(chore_handle *h, const float *df, int df_idx, float threshold, float filter_val, const float *surf,
+                      const float *samples, const float *pca, const float *parts, const float *centers, int B, int N,
+                      int cap, int append, float *out_points, int32_t *out_labels, float *out_pca, float *out_centers,
+                      int32_t *out_count, float *packed, int32_t *iter_count, void *stream);
+/* next samples (:164-177): image b with more than one hit draws sample_num of its packed hits uniformly and adds
+ * N(0, sigma_hit^2) noise, otherwise it restarts from samples_init (B,Ninit,3) + N(0, sigma_miss^2).  Random numbers:
+ * Philox4x32-10 with (seed, subsequence = b * sample_num + j, offset) -- or, when `uniforms` (B,sample_num) in [0,1) and
+ * `normals` (B,sample_num,3) are given, those (index = floor(u * count)). */
+int chore_gen_resample(chore_handle *h, const float *packed, const int32_t *iter_count, const float *samples_init, int B,
+                       int N, int Ninit, int sample_num, float sigma_hit, float sigma_miss, uint64_t seed, uint64_t offset,
+                       const float *uniforms, const float *normals, float *out, void *stream);
+/* samples_count[0] += min_b iter_count[b]   (:160) */
+int chore_gen_total(chore_handle *h, const int32_t *iter_count, int B, int32_t *samples_count, void *stream);
+/* compose_outdict (:190-217): pca_mean (B,9) / centers_mean (B,6) = mean over the first samples_count[0] kept points */
+int chore_gen_finalize(chore_handle *h, const float *out_pca, const float *out_centers, int B, int cap,
+                       const int32_t *samples_count, float *pca_mean, float *centers_mean, void *stream);
+
 /* torch.optim.Adam.step (weight_decay 0, amsgrad off) for up to CHORE_ADAM_MAX_ENTRIES small tensors in one
  * launch.  `step` is a device int32 step counter (read, then incremented by the kernel: graph-replay safe).
  * The reference fitting loops call zero_grad() once per OUTER iteration and loss.backward() in every inner step

@@ -14,8 +14,8 @@ from oracle.analytic_field import AnalyticField
 
 def run_ours(df_type, seed, init, num_points, num_steps):
     import chore_b200
-    gen = chore_b200.Generator(AnalyticField(), device="cpu")
-    assert gen.threshold == 2.0 and gen.filter_val == 0.004
+    gen = chore_b200.Generator(AnalyticField(), threshold=2.0, filter_val=0.004, device="cpu")
+    assert chore_b200.Generator(AnalyticField(), device="cpu").filter_val == 0.03      # the reference's defaults (generator.py:18-26)
     torch.manual_seed(seed)
     drawn = gen.init_samples(3000, batch_size=2)                 # consumes the generator like the reference's call did
     drawn[1] = drawn[0].flip(0)
@@ -48,7 +48,7 @@ def test_gen_pc_batch_equals_live_reference():
     init = ref.init_samples(2000, batch_size=1)
     want = ref.gen_pc_batch(AnalyticField(), "object", init, 21000, {"crop_center": torch.tensor([[1008., 995.]])}, 6, mute=True)
     import chore_b200
-    gen = chore_b200.Generator(AnalyticField(), device="cpu")
+    gen = chore_b200.Generator(AnalyticField(), threshold=2.0, filter_val=0.004, device="cpu")
     torch.manual_seed(5)
     init2 = gen.init_samples(2000, batch_size=1)
     assert torch.equal(init, init2)

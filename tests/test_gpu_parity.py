@@ -183,7 +183,7 @@ def test_approx_surface_vs_golden(net, sd):
     g = load_golden("approx_surface.npz")
     feat, tmpx = O.synth_features(int(g["seed"]), B=1)
     set_maps(net, feat, tmpx)
-    gen = chore_b200.Generator(net, device=DEV)
+    gen = chore_b200.Generator(net, threshold=2.0, filter_val=0.004, device=DEV)
     cc = T(g["crop_center"])
     s0 = O.synth_points("frustum", 32, 1, 512).to(DEV).requires_grad_(True)
     samples, preds = gen.approx_surface(net, s0, 10, {"crop_center": cc}, "human")
@@ -654,6 +654,97 @@ def test_fused_fit_loop_matches_reference_loop_semantics(net, smpl_layer):
     assert rel_err(0.5 * fh._g_pose_full[:, 66:], sh.hand_pose.grad) < 1e-4, rel_err(0.5 * fh._g_pose_full[:, 66:], sh.hand_pose.grad)
 
 
+def test_generator_device_kernels(net):
+    """csrc/generator.cu against torch: ordered compaction == boolean-mask indexing, resampling == the reference's formula for
+    given draws, Philox draws reproducible and in range, finalize == mean over the kept prefix."""
+    h = net.handle
+    g = torch.Generator().manual_seed(11)
+    B, N, cap = 3, 5000, 6000
+    df = torch.rand(B, 2, N, generator=g).to(DEV) * 0.02
+    df[2] = 1.0                                   # image 2: no hit at all
+    df[2, 1, 77] = 0.0                            # ... except one (the reference's "<= 1 hit" fallback)
+    surf, samples = torch.randn(B, N, 3, generator=g).to(DEV), torch.randn(B, N, 3, generator=g).to(DEV)
+    pca, parts, cen = torch.randn(B, 9, N, generator=g).to(DEV), torch.randn(B, 14, N, generator=g).to(DEV), torch.randn(B, 6, N, generator=g).to(DEV)
+    out = (torch.zeros(B, cap, 3, device=DEV), torch.zeros(B, cap, dtype=torch.int32, device=DEV), torch.zeros(B, cap, 9, device=DEV),
+           torch.zeros(B, cap, 6, device=DEV), torch.zeros(B, dtype=torch.int32, device=DEV))
+    packed, cnt = torch.zeros(B, N, 3, device=DEV), torch.zeros(B, dtype=torch.int32, device=DEV)
+    total = torch.zeros(1, dtype=torch.int32, device=DEV)
+    for rep in range(2):                          # two appends: the second lands behind the first
+        h.gen_compact(df, 1, 2.0, 0.01, samples, packed, cnt, surf=surf, preds=(pca, parts, cen), out=out)
+        h.gen_total(cnt, total)
+    mask = torch.clamp(df[:, 1], max=2.0) < 0.01
+    for b in range(B):
+        m = mask[b]
+        k = int(m.sum())
+        assert int(cnt[b]) == k and int(out[4][b]) == min(cap, 2 * k)
+        assert torch.equal(packed[b, :k], samples[b, m])
+        for rep in range(2):
+            lo, hi = rep * k, min(cap, (rep + 1) * k)
+            assert torch.equal(out[0][b, lo:hi], surf[b, m][:hi - lo])
+            assert torch.equal(out[1][b, lo:hi].long(), parts[b][:, m].argmax(0)[:hi - lo])
+            assert torch.equal(out[2][b, lo:hi], pca[b][:, m].t()[:hi - lo]) and torch.equal(out[3][b, lo:hi], cen[b][:, m].t()[:hi - lo])
+    assert int(total) == 2 * int(mask.sum(1).min())
+    pm, cm = h.gen_finalize(out[2], out[3], total)
+    n = int(total)
+    assert rel_err(pm, out[2][:, :n].mean(1)) < 1e-5 and rel_err(cm, out[3][:, :n].mean(1)) < 1e-5
+    # resampling with given draws: hit images pick packed[floor(u * count)], the starved image restarts from the initial samples
+    S = 4000
+    init = torch.randn(B, 300, 3, generator=g).to(DEV)
+    u, nrm = torch.rand(B, S, generator=g).to(DEV), torch.randn(B, S, 3, generator=g).to(DEV)
+    new = h.gen_resample(packed, cnt, init, S, 2.0 / 3, 0.5, 0, 0, u, nrm)
+    for b in range(B):
+        k = int(cnt[b])
+        want = packed[b][(u[b] * k).long().clamp(max=k - 1)] + (2.0 / 3) * nrm[b] if k > 1 else init[b][(u[b] * 300).long().clamp(max=299)] + 0.5 * nrm[b]
+        assert torch.equal(new[b], want), b
+    # Philox: reproducible for (seed, offset), different otherwise, noise of the right scale, every sample near a hit
+    a1 = h.gen_resample(packed, cnt, init, S, 0.0, 0.0, 5, 3)
+    a2 = h.gen_resample(packed, cnt, init, S, 0.0, 0.0, 5, 3)
+    a3 = h.gen_resample(packed, cnt, init, S, 0.0, 0.0, 5, 4)
+    assert torch.equal(a1, a2) and not torch.equal(a1, a3)
+    k0 = int(cnt[0])
+    same = (a1[0][:, None, :] == packed[0, :k0][None]).all(-1)      # (S, hits): exact row matches
+    assert bool(same.any(1).all())                                 # sigma = 0: every new sample IS one of the hits
+    assert same.float().argmax(1).unique().numel() > 0.5 * min(k0, S)              # ... spread over the hits
+    noisy = h.gen_resample(packed, cnt, init, S, 2.0 / 3, 0.5, 5, 3)
+    assert abs(float((noisy[0] - a1[0]).std()) - 2.0 / 3) < 0.03 and abs(float((noisy[2] - a1[2]).std()) - 0.5) < 0.03
+
+
+def test_generator_device_loop_equals_reference_order_loop(net):
+    """Generator(rng='device') == Generator(rng='reference') when the device loop is fed the reference loop's own draws (torch CPU
+    generator, randint then randn per image and outer iteration, recon/generator.py:166-176): same points, labels, means."""
+    import chore_b200
+    feat, tmpx = O.synth_features(83, B=2)
+    set_maps(net, feat, tmpx)
+    cc = torch.tensor([[1008., 995.], [1000., 990.]], device=DEV)
+    S = 2000
+    host = chore_b200.Generator(net, threshold=2.0, filter_val=10.0, device=DEV)
+    devg = chore_b200.Generator(net, threshold=2.0, filter_val=10.0, device=DEV, rng="device")
+    torch.manual_seed(3)
+    init = host.init_samples(3000, batch_size=2)
+    torch.manual_seed(4)
+    want = host.gen_pc_batch(net, "object", init, 5000, {"crop_center": cc}, num_steps=2, sample_num=S)
+
+    def draws(it, iter_count):                    # what the reference loop draws, in its order
+        us, ns = [], []
+        for k in iter_count.tolist():
+            n = k if k > 1 else init.shape[1]
+            idx = torch.randint(n, (S,))
+            us.append((idx.double() + 0.5) / n)
+            ns.append(torch.randn(1, S, 3)[0])
+        return torch.stack(us).float().to(DEV), torch.stack(ns).to(DEV)
+
+    torch.manual_seed(4)
+    got = devg._gen_pc_batch_device(net, "object", init, 5000, {"crop_center": cc}, 2, 100, S, randoms=draws)
+    assert got["points"].shape == want["points"].shape and got["parts"].dtype == torch.int64
+    assert torch.equal(got["points"].cpu(), want["points"]) and torch.equal(got["parts"].cpu(), want["parts"])
+    assert rel_err(got["pca_axis"], want["pca_axis"]) < 1e-5 and rel_err(got["centers"], want["centers"]) < 1e-5
+    # and the stand-alone device loop (Philox draws) runs, is reproducible for a seed and fills the request
+    torch.manual_seed(3)
+    a = devg.gen_pc_batch(net, "human", init, 5000, {"crop_center": cc}, num_steps=2, sample_num=S)
+    b = devg.gen_pc_batch(net, "human", init, 5000, {"crop_center": cc}, num_steps=2, sample_num=S)
+    assert a["points"].shape[1] >= 5000 and torch.equal(a["points"], b["points"]) and a["centers"].shape == (2, 6)
+
+
 def test_generator_gen_pc_batch_mechanics(net):
     """Generator.gen_pc_batch (recon/generator.py:123-217) on-device: projection steps, surface filter, resampling and
     the final argmax / mean reductions.  With random weights the field is not a distance field, so the filter value is
@@ -661,7 +752,7 @@ def test_generator_gen_pc_batch_mechanics(net):
     import chore_b200
     feat, tmpx = O.synth_features(81, B=2)
     set_maps(net, feat, tmpx)
-    gen = chore_b200.Generator(net, filter_val=10.0, device=DEV)
+    gen = chore_b200.Generator(net, threshold=2.0, filter_val=10.0, device=DEV)
     cc = torch.tensor([[1008., 995.], [1000., 990.]], device=DEV)
     torch.manual_seed(0)
     init = gen.init_samples(3000, batch_size=2)
@@ -883,7 +974,7 @@ def test_fused_surface_projection_matches_autograd_path(net):
     cc = torch.tensor([[1008., 995.], [1000., 990.]], device=DEV)
     q = {"crop_center": cc}
     pts = O.synth_points("frustum", 112, 2, 3000).to(DEV)
-    fused, plain = chore_b200.Generator(net, device=DEV, fused=True), chore_b200.Generator(net, device=DEV, fused=False)
+    fused, plain = chore_b200.Generator(net, threshold=2.0, device=DEV, fused=True), chore_b200.Generator(net, threshold=2.0, device=DEV, fused=False)
     for df_type in ("human", "object"):
         a, pa = fused.approx_surface(net, pts.clone().requires_grad_(True), 1, q, df_type)
         b, pb = plain.approx_surface(net, pts.clone().requires_grad_(True), 1, q, df_type)
