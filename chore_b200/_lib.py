@@ -64,6 +64,8 @@ SIGNATURES = {
     "chore_add_rowvec": (_I, [_P, _P, _P, _I, _I, _F, _P]),
     "chore_surface_clamp_grad": (_I, [_P, _P, _I, _F, _I, _I, _P, _P]),
     "chore_surface_step": (_I, [_P, _P, _P, _P, _I, _F, _I, _I, _P, _P]),
+    "chore_contact_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
+    "chore_contact_loss": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "chore_gen_compact": (_I, [_P, _P, _I, _F, _F, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "chore_gen_resample": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _F, C.c_uint64, C.c_uint64, _P, _P, _P, _P]),
     "chore_gen_total": (_I, [_P, _P, _I, _P, _P]),
@@ -356,6 +358,23 @@ class Handle:
             self._check(self.lib.chore_surface_step(self.h, points.data_ptr(), g_points.data_ptr(), df.data_ptr(), df_idx, threshold,
                                                     points.shape[0], points.shape[1], out.data_ptr(), _stream()))
         return out
+
+    # ---- joint-phase contact term (csrc/contact.cu) ----------------------------------------------------
+    def contact_loss(self, smpl_verts, obj, df_hum_o, df_obj_h, part_o, part_labels, thresh: float = 0.08, want_grads: bool = True):
+        """-> (loss (1,), n_pairs (1,) int32, g_smpl, g_obj)"""
+        check_cuda(smpl_verts, obj, df_hum_o, df_obj_h, part_o)
+        B, Nh, No = smpl_verts.shape[0], smpl_verts.shape[1], obj.shape[1]
+        dev = obj.device
+        loss, pairs = torch.zeros(1, device=dev), torch.zeros(1, dtype=torch.int32, device=dev)
+        g_s = torch.empty_like(smpl_verts) if want_grads else None
+        g_o = torch.empty_like(obj) if want_grads else None
+        nbytes = int(self.lib.chore_contact_workspace_bytes(B, Nh, No))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.chore_contact_loss(self.h, smpl_verts.data_ptr(), obj.data_ptr(), df_hum_o.data_ptr(), df_obj_h.data_ptr(),
+                                                    part_o.data_ptr(), part_labels.data_ptr(), B, Nh, No, thresh, loss.data_ptr(),
+                                                    pairs.data_ptr(), _ptr(g_s), _ptr(g_o), ws.data_ptr(), nbytes, _stream()))
+        return loss, pairs, g_s, g_o
 
     # ---- generator bookkeeping (csrc/generator.cu) --------------------------------------------------
     def gen_compact(self, df, df_idx, threshold, filter_val, samples, packed, iter_count, surf=None, preds=None, out=None) -> None:

@@ -99,7 +99,7 @@ __device__ __forceinline__ void umma_burst(uint32_t d_tmem, uint64_t ah, uint64_
             "tcgen05.mma.cta_group::1.kind::f16 [%0], a, d, %5, q;\n"
             "}" ::"r"(d_tmem), "l"(ah), "l"(al), "l"(wh), "l"(wl), "r"(idesc) : "memory");
 }
-__device__ __forceinline__ uint64_t desc64(uint32_t saddr, uint32_t hi) { return ((uint64_t)hi << 32) | (uint64_t)desc_lo(saddr); }
+__device__ __forceinline__ uint64_t desc64a(uint32_t saddr, uint32_t hi) { return ((uint64_t)hi << 32) | (uint64_t)desc_lo(saddr); }
 
 // GroupNorm sums of one transposed 32 x 32 chunk: this lane holds the channel quad starting at absolute channel `c` for
 // 8 rows (pixv[i] < 0: row outside the image).  Rows are summed in the thread, the 4 lanes that share a quad with two
@@ -230,12 +230,12 @@ __global__ void __launch_bounds__(kThreadsHx, 1) conv_hx_kernel(const HxParams p
                 tc_fence_after();
                 const bool full = a.Cin - kb * 64 >= 64;
                 int ky = tap / KS, kx = tap - ky * KS;
-                uint64_t ah = desc64(smem_u32(halo) + hs * halo_stage + (uint32_t)((ky * kPitch + kx) * 128), a_hi);
+                uint64_t ah = desc64a(smem_u32(halo) + hs * halo_stage + (uint32_t)((ky * kPitch + kx) * 128), a_hi);
                 for (; tap < kTaps && left > 0; ++tap, --left) {
                     mbar_wait(&ctl->w_full[s], wph);
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint64_t wh = desc64(w0 + s * p.w_slot, kDescHi);
+                        const uint64_t wh = desc64a(w0 + s * p.w_slot, kDescHi);
                         if (full) umma_burst<4>(d, ah, ah + lo_plane, wh, wh + lo_panel, idesc, first);
                         else umma_burst<2>(d, ah, ah + lo_plane, wh, wh + lo_panel, idesc, first);
                         umma_commit(&ctl->w_empty[s]);

@@ -65,7 +65,11 @@ __global__ void __launch_bounds__(kThreadsFwd, 1) query_tc_kernel(const TcParams
 #define DBG(i) (dbg_on ? &dbg_local[i] : nullptr)
 
     if (threadIdx.x == 0) {
-        const int n_issuers = ((q.head_mask & 5u) != 0) + ((q.head_mask & 10u) != 0);     // an A stage is released by every issuer that reads it
+        // an A stage is released by every issuer that reads it.  Three active heads run on ONE issuer: with two issuers sharing the
+        // weight ring in global panel order, a 2 + 1 split of the heads can deadlock (issuer A waits for a ring slot that holds a panel
+        // of issuer B, B waits for the epilogue, the epilogue for an accumulator of A) -- seen as size-dependent hangs for masks
+        // 7 / 11 / 13 / 14; the 2 + 2 and 1 + 1 alternations are symmetric and never build that cycle.
+        const int n_issuers = __popc(q.head_mask) == 3 ? 1 : ((q.head_mask & 5u) != 0) + ((q.head_mask & 10u) != 0);
         for (int i = 0; i < kNA; ++i) { mbar_init(&bars->a_full[i], 4); mbar_init(&bars->a_empty[i], n_issuers); }
         for (int i = 0; i < kNW; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
         for (int i = 0; i < kNACT; ++i) { mbar_init(&bars->act_full[i], 4); mbar_init(&bars->act_empty[i], 1); }
@@ -112,7 +116,7 @@ __global__ void __launch_bounds__(kThreadsFwd, 1) query_tc_kernel(const TcParams
         // instructions themselves are predicated on one elected lane.  Warp 1 issues for heads 0 and 2, warp 14 for heads
         // 1 and 3 (consecutive steps alternate between the issuers); both walk the same global sequence of weight panels /
         // activation blocks and skip the other's entries.
-        const unsigned my_heads = q.head_mask & (warp == 1 ? 5u : 10u);
+        const unsigned my_heads = __popc(q.head_mask) == 3 ? (warp == 1 ? q.head_mask : 0u) : (q.head_mask & (warp == 1 ? 5u : 10u));
         constexpr uint32_t idesc = make_idesc(kTileM, 128), idesc16 = make_idesc(kTileM, 16);
         const uint32_t ringA_lo = desc_lo(smem_u32(ringA)), ringAct_lo = desc_lo(smem_u32(ringAct)), ringW_lo = desc_lo(smem_u32(ringW));
         constexpr uint32_t kStageLo = kStageA >> 4, kPanelLo = kPanelBytes >> 4;
@@ -143,15 +147,8 @@ __global__ void __launch_bounds__(kThreadsFwd, 1) query_tc_kernel(const TcParams
                     tc_fence_after();
                     const uint32_t w0 = ringW_lo + s0 * kPanelLo;
                     if (elect_one()) {
-                        umma_f16(d, a_hi, w0, idesc, kb != 0);
-                        umma_f16(d, a_lo, w0, idesc, 1);
-                        if (!last) {
-#pragma unroll
-                            for (int ks = 1; ks < 4; ++ks) {
-                                umma_f16(d, a_hi + 2 * ks, w0 + 2 * ks, idesc, 1);
-                                umma_f16(d, a_lo + 2 * ks, w0 + 2 * ks, idesc, 1);
-                            }
-                        }
+                        if (!last) umma_burst_pair<4>(d, desc64(a_hi), desc64(a_lo), desc64(w0), idesc, kb != 0);
+                        else umma_burst_pair<1>(d, desc64(a_hi), desc64(a_lo), desc64(w0), idesc, kb != 0);
                         umma_commit(&bars->w_empty[s0]);
                     }
                     __syncwarp();
@@ -159,11 +156,8 @@ __global__ void __launch_bounds__(kThreadsFwd, 1) query_tc_kernel(const TcParams
                     tc_fence_after();
                     const uint32_t w1 = ringW_lo + s1 * kPanelLo;
                     if (elect_one()) {
-                        umma_f16(d, a_hi, w1, idesc, 1);
-                        if (!last) {
-#pragma unroll
-                            for (int ks = 1; ks < 4; ++ks) umma_f16(d, a_hi + 2 * ks, w1 + 2 * ks, idesc, 1);
-                        }
+                        if (!last) umma_burst_single<4>(d, desc64(a_hi), desc64(w1), idesc);
+                        else umma_burst_single<1>(d, desc64(a_hi), desc64(w1), idesc);
                         umma_commit(&bars->w_empty[s1]);
                         if (last) umma_commit(&bars->tm_full[h]);       // layer-1 accumulator of head h complete
                         if (h == last_head) umma_commit(&bars->a_empty[sa]);
@@ -195,13 +189,7 @@ __global__ void __launch_bounds__(kThreadsFwd, 1) query_tc_kernel(const TcParams
                             tc_fence_after();
                             const uint32_t w0 = ringW_lo + s0 * kPanelLo;
                             if (elect_one()) {
-                                umma_f16(d, a_hi, w0, idesc, kb != 0);
-                                umma_f16(d, a_lo, w0, idesc, 1);
-#pragma unroll
-                                for (int ks = 1; ks < 4; ++ks) {
-                                    umma_f16(d, a_hi + 2 * ks, w0 + 2 * ks, idesc, 1);
-                                    umma_f16(d, a_lo + 2 * ks, w0 + 2 * ks, idesc, 1);
-                                }
+                                umma_burst_pair<4>(d, desc64(a_hi), desc64(a_lo), desc64(w0), idesc, kb != 0);
                                 umma_commit(&bars->w_empty[s0]);
                             }
                             __syncwarp();
@@ -209,8 +197,7 @@ __global__ void __launch_bounds__(kThreadsFwd, 1) query_tc_kernel(const TcParams
                             tc_fence_after();
                             const uint32_t w1 = ringW_lo + s1 * kPanelLo;
                             if (elect_one()) {
-#pragma unroll
-                                for (int ks = 0; ks < 4; ++ks) umma_f16(d, a_hi + 2 * ks, w1 + 2 * ks, idesc, 1);
+                                umma_burst_single<4>(d, desc64(a_hi), desc64(w1), idesc);
                                 umma_commit(&bars->w_empty[s1]);
                                 umma_commit(&bars->act_empty[sa]);
                                 if (kb == 1) umma_commit(&bars->tm_full[h]);
@@ -230,12 +217,7 @@ __global__ void __launch_bounds__(kThreadsFwd, 1) query_tc_kernel(const TcParams
                             for (int kb = 0; kb < 2; ++kb) {
                                 const uint32_t a_hi = ringAct_lo + (kb == 0 ? sa0 : sa1) * kStageLo, a_lo = a_hi + kPanelLo;
                                 const uint32_t w_hi = w + kb * (4096 >> 4), w_lo = w_hi + (2048 >> 4);
-#pragma unroll
-                                for (int ks = 0; ks < 4; ++ks) {
-                                    umma_f16(d, a_hi + 2 * ks, w_hi + 2 * ks, idesc16, (kb | ks) != 0);
-                                    umma_f16(d, a_lo + 2 * ks, w_hi + 2 * ks, idesc16, 1);
-                                    umma_f16(d, a_hi + 2 * ks, w_lo + 2 * ks, idesc16, 1);
-                                }
+                                umma_burst_triple4(d, desc64(a_hi), desc64(a_lo), desc64(w_hi), desc64(w_lo), idesc16, kb != 0);
                                 umma_commit(&bars->act_empty[kb == 0 ? sa0 : sa1]);
                             }
                             umma_commit(&bars->w_empty[s0]);
@@ -482,17 +464,16 @@ __global__ void __launch_bounds__(kThreads, 1) query_bwd_tc_kernel(const TcParam
             mbar_wait(&bars->w_full[s0], (u / kBwdNW) & 1);
             const uint32_t w0 = ringW_lo + s0 * kPanelLo;
             if (elect_one()) {
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    umma_f16(d, a_hi + 2 * ks, w0 + 2 * ks, idesc, !(first && ks == 0));
-                    umma_f16(d, a_lo + 2 * ks, w0 + 2 * ks, idesc, 1);
-                }
+                if (ksteps == 4) umma_burst_pair<4>(d, desc64(a_hi), desc64(a_lo), desc64(w0), idesc, !first);
+                else umma_burst_pair<1>(d, desc64(a_hi), desc64(a_lo), desc64(w0), idesc, !first);
                 umma_commit(&bars->w_empty[s0]);
             }
             __syncwarp();
             mbar_wait(&bars->w_full[s1], ((u + 1) / kBwdNW) & 1);
             const uint32_t w1 = ringW_lo + s1 * kPanelLo;
             if (elect_one()) {
-                for (int ks = 0; ks < ksteps; ++ks) umma_f16(d, a_hi + 2 * ks, w1 + 2 * ks, idesc, 1);
+                if (ksteps == 4) umma_burst_single<4>(d, desc64(a_hi), desc64(w1), idesc);
+                else umma_burst_single<1>(d, desc64(a_hi), desc64(w1), idesc);
                 umma_commit(&bars->w_empty[s1]);
             }
             __syncwarp();

@@ -62,6 +62,62 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint32_t a_lo, uint32_
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n}"
                  ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi) : "memory");
 }
+// ---- MMA bursts --------------------------------------------------------------------------------------------------------
+// The thread that issues tcgen05.mma is held until the tensor pipe takes the instruction, and whatever it executes between
+// two MMAs is added to the math time (profiles/mma_microbench_r1.txt).  These helpers issue a whole group of MMAs from ONE
+// asm block: 64-bit descriptors come in as operands, the per-k-step advance (+2 in the low word = 32 bytes inside the
+// swizzle atom) is a single add, and there is one predicate set-up per block instead of one per instruction.
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi = kDescHi) { return ((uint64_t)hi << 32) | (uint64_t)lo; }
+
+#define CHORE_MMA(D, A, B, I, P) "tcgen05.mma.cta_group::1.kind::f16 [" D "], " A ", " B ", " I ", " P ";\n"
+// for ks < KSN: D (+)= A0[ks] * W[ks];  D += A1[ks] * W[ks]      (the hi weight panel against the hi and lo activations)
+template <int KSN>
+__device__ __forceinline__ void umma_burst_pair(uint32_t d, uint64_t a0, uint64_t a1, uint64_t w, uint32_t idesc, uint32_t acc_first) {
+    static_assert(KSN == 1 || KSN == 4, "k steps per block");
+    if (KSN == 1)
+        asm volatile("{\n.reg .pred p, q;\nsetp.ne.b32 p, %5, 0;\nsetp.eq.b32 q, %4, %4;\n"
+                     CHORE_MMA("%0", "%1", "%3", "%4", "p") CHORE_MMA("%0", "%2", "%3", "%4", "q")
+                     "}" ::"r"(d), "l"(a0), "l"(a1), "l"(w), "r"(idesc), "r"(acc_first) : "memory");
+    else
+        asm volatile("{\n.reg .pred p, q;\n.reg .b64 x, y, z;\nsetp.ne.b32 p, %5, 0;\nsetp.eq.b32 q, %4, %4;\n"
+                     CHORE_MMA("%0", "%1", "%3", "%4", "p") CHORE_MMA("%0", "%2", "%3", "%4", "q")
+                     "add.s64 x, %1, 2;\nadd.s64 y, %2, 2;\nadd.s64 z, %3, 2;\n"
+                     CHORE_MMA("%0", "x", "z", "%4", "q") CHORE_MMA("%0", "y", "z", "%4", "q")
+                     "add.s64 x, %1, 4;\nadd.s64 y, %2, 4;\nadd.s64 z, %3, 4;\n"
+                     CHORE_MMA("%0", "x", "z", "%4", "q") CHORE_MMA("%0", "y", "z", "%4", "q")
+                     "add.s64 x, %1, 6;\nadd.s64 y, %2, 6;\nadd.s64 z, %3, 6;\n"
+                     CHORE_MMA("%0", "x", "z", "%4", "q") CHORE_MMA("%0", "y", "z", "%4", "q")
+                     "}" ::"r"(d), "l"(a0), "l"(a1), "l"(w), "r"(idesc), "r"(acc_first) : "memory");
+}
+// for ks < KSN: D += A[ks] * W[ks]      (the lo weight panel against the hi activations)
+template <int KSN>
+__device__ __forceinline__ void umma_burst_single(uint32_t d, uint64_t a, uint64_t w, uint32_t idesc) {
+    static_assert(KSN == 1 || KSN == 4, "k steps per block");
+    if (KSN == 1)
+        asm volatile("{\n.reg .pred q;\nsetp.eq.b32 q, %3, %3;\n" CHORE_MMA("%0", "%1", "%2", "%3", "q")
+                     "}" ::"r"(d), "l"(a), "l"(w), "r"(idesc) : "memory");
+    else
+        asm volatile("{\n.reg .pred q;\n.reg .b64 x, z;\nsetp.eq.b32 q, %3, %3;\n"
+                     CHORE_MMA("%0", "%1", "%2", "%3", "q")
+                     "add.s64 x, %1, 2;\nadd.s64 z, %2, 2;\n" CHORE_MMA("%0", "x", "z", "%3", "q")
+                     "add.s64 x, %1, 4;\nadd.s64 z, %2, 4;\n" CHORE_MMA("%0", "x", "z", "%3", "q")
+                     "add.s64 x, %1, 6;\nadd.s64 z, %2, 6;\n" CHORE_MMA("%0", "x", "z", "%3", "q")
+                     "}" ::"r"(d), "l"(a), "l"(w), "r"(idesc) : "memory");
+}
+// for ks < 4: D (+)= Ah[ks] * Wh[ks];  D += Al[ks] * Wh[ks];  D += Ah[ks] * Wl[ks]      (one 64-channel block, 3-term split)
+__device__ __forceinline__ void umma_burst_triple4(uint32_t d, uint64_t ah, uint64_t al, uint64_t wh, uint64_t wl, uint32_t idesc,
+                                                   uint32_t acc_first) {
+    asm volatile("{\n.reg .pred p, q;\n.reg .b64 a, b, c, e;\nsetp.ne.b32 p, %6, 0;\nsetp.eq.b32 q, %5, %5;\n"
+                 CHORE_MMA("%0", "%1", "%3", "%5", "p") CHORE_MMA("%0", "%2", "%3", "%5", "q") CHORE_MMA("%0", "%1", "%4", "%5", "q")
+                 "add.s64 a, %1, 2;\nadd.s64 b, %2, 2;\nadd.s64 c, %3, 2;\nadd.s64 e, %4, 2;\n"
+                 CHORE_MMA("%0", "a", "c", "%5", "q") CHORE_MMA("%0", "b", "c", "%5", "q") CHORE_MMA("%0", "a", "e", "%5", "q")
+                 "add.s64 a, %1, 4;\nadd.s64 b, %2, 4;\nadd.s64 c, %3, 4;\nadd.s64 e, %4, 4;\n"
+                 CHORE_MMA("%0", "a", "c", "%5", "q") CHORE_MMA("%0", "b", "c", "%5", "q") CHORE_MMA("%0", "a", "e", "%5", "q")
+                 "add.s64 a, %1, 6;\nadd.s64 b, %2, 6;\nadd.s64 c, %3, 6;\nadd.s64 e, %4, 6;\n"
+                 CHORE_MMA("%0", "a", "c", "%5", "q") CHORE_MMA("%0", "b", "c", "%5", "q") CHORE_MMA("%0", "a", "e", "%5", "q")
+                 "}" ::"r"(d), "l"(ah), "l"(al), "l"(wh), "l"(wl), "r"(idesc), "r"(acc_first) : "memory");
+}
+
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));

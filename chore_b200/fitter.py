@@ -12,8 +12,8 @@ Mirrors, with the same names and argument meaning (paths relative to /root/refer
   ReconFitterBehave.get_loss_weights, forward_step ('object only'), forward_smpl (all terms),
       optimize_smpl, optimize_smpl_object ('object only' phase)
       recon/recon_fit_behave.py:90-163,165-222,224-358
-Out of scope: the silhouette phase (neural_renderer + detectron2) and the
-joint-phase contact / collision terms (pytorch3d, torch-mesh-isect).
+The joint-phase contact term (pytorch3d Chamfer in the reference) is csrc/contact.cu; the silhouette phase lives in
+silhouette.py; the interpenetration term (torch-mesh-isect, not vendored by the reference) is a plug-in hook.
 """
 from __future__ import annotations
 
@@ -53,6 +53,23 @@ class _So3Fn(torch.autograd.Function):
     def backward(ctx, g_out):
         (m,) = ctx.saved_tensors
         return ctx.handle.project_so3_bwd(m, g_out), None
+
+
+class _ContactFn(torch.autograd.Function):
+    """chore_contact_loss with its closed-form gradients to the object points and the SMPL vertices."""
+
+    @staticmethod
+    def forward(ctx, obj, smpl_verts, df_hum_o, df_obj_h, part_o, part_labels, handle):
+        args = [x.detach().contiguous().float() for x in (smpl_verts, obj, df_hum_o, df_obj_h, part_o)]
+        loss, pairs, g_s, g_o = handle.contact_loss(*args, part_labels.to(torch.int32).contiguous())
+        ctx.save_for_backward(g_s, g_o)
+        ctx.mark_non_differentiable(pairs)
+        return loss[0], pairs
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_pairs):
+        g_s, g_o = ctx.saved_tensors
+        return g_o * g_loss, g_s * g_loss, None, None, None, None, None
 
 
 class MahalanobisPrior:
@@ -234,6 +251,39 @@ class ReconFitterBase:
         loss_dict["df_h"] = torch.clamp(df_pred[:, 0:1, :], max=0.1).mean()
         return df_pred, parts_pred, centers_pred
 
+    def compute_contact_loss(self, df_hum_o, df_obj_h, object, smpl_verts, loss_dict, part_o=None):
+        """recon_fit_base.py:553-608: pull the contact points (cross distance field < 0.08 m) of matching SMPL parts together
+        (part-wise Chamfer distance, csrc/contact.cu).  Needs `self.part_labels` ((6890,) part index per SMPL vertex,
+        load_part_labels :277-287).  Adds nothing when no contact is found, like the reference (one host sync for that test)."""
+        if getattr(self, "part_labels", None) is None:
+            raise RuntimeError("compute_contact_loss needs fitter.part_labels (6890 part indices, assets/smpl_parts_dense.pkl)")
+        loss, pairs = _ContactFn.apply(object, smpl_verts, df_hum_o, df_obj_h, part_o, self.part_labels.to(object.device),
+                                       _lib.get_handle(object.device))
+        if int(pairs) == 0:
+            if self.debug:
+                print("no contact")
+            return
+        loss_dict["contact"] = loss
+
+    def compute_collision_loss(self, smpl_verts, smpl_faces, obj_R, obj_t, obj_s):
+        """recon_fit_base.py:610-642 is torch-mesh-isect's BVH + DistanceFieldPenetrationLoss (third-party CUDA, source not under
+        the reference tree, no pinned version): not restated here.  Plug it in with `fitter.collision_fn = callable(smpl_verts,
+        smpl_faces, obj_R, obj_t, obj_s) -> scalar`; without one the 'collide' term is left out (its weight is 3^2 / (1 + decay)
+        against 30^2 for contact)."""
+        fn = getattr(self, "collision_fn", None)
+        return None if fn is None else fn(smpl_verts, smpl_faces, obj_R, obj_t, obj_s)
+
+    @staticmethod
+    def load_part_labels(assets_root: str, device="cpu") -> torch.Tensor:
+        """(6890,) part index per SMPL vertex from smpl_parts_dense.pkl (recon_fit_base.py:277-287; dict order = label)."""
+        import pickle as pkl
+        from os.path import join
+        d = pkl.load(open(join(assets_root, "smpl_parts_dense.pkl"), "rb"), encoding="latin1")
+        labels = torch.zeros(6890, dtype=torch.int32)
+        for n, k in enumerate(d):
+            labels[torch.as_tensor(d[k]).long()] = n
+        return labels.to(device)
+
     def compute_prior_loss(self, loss_dict, smpl, nobeta: bool = False):
         """recon_fit_base.py:522-535 with the priors loaded once (self.priors)."""
         if self.priors is None:
@@ -321,20 +371,41 @@ class ReconFitterBehave(ReconFitterBase):
         return {k: (lambda cst, it, c=c: c * cst / (1 + it)) for k, c in w.items()}
 
     def forward_step(self, model, smpl, data_dict, obj_R, obj_t, obj_s, phase, noise=None):
-        """recon_fit_behave.py:165-222 for phase 'object only' (the reference's double query of the
-        object points, :179 + recon_fit_base.py:515, is kept so results and cost are comparable)."""
-        if phase != "object only":
-            raise NotImplementedError(f"phase {phase!r} needs the silhouette renderer / contact terms (out of scope)")
+        """recon_fit_behave.py:165-222, all three phases.  'object only': object / scale / ocent (the reference's double query of
+        the object points, :179 + recon_fit_base.py:515, is kept so results and cost are comparable).  'sil': the occlusion-aware
+        silhouette term of data_dict['silhouette'] (SilLossROI) + scale / trans regularisers.  'joint': 'object only' + the
+        contact term + (when a collision_fn is plugged in) the interpenetration term."""
+        if phase not in ("object only", "sil", "joint"):
+            raise ValueError(f"unknown phase {phase!r}")
         loss_dict = {}
         R = self.decopose_axis(obj_R, noise=noise)
         object = self.transform_obj_verts(data_dict["objects"], R, obj_t, obj_s)
-        with heads(model, _lib.HEAD_CENTERS):
+        need = _lib.HEAD_CENTERS | ((_lib.HEAD_DF | _lib.HEAD_PARTS) if phase == "joint" else 0)
+        with heads(model, need):
             model.query(object, **data_dict["query_dict"])
-        centers_pred_o = model.get_preds()[3]
+        preds = model.get_preds()
+        df_pred, part_o, centers_pred_o = preds[0], preds[2], preds[3]
         obj_center_pred = data_dict["smpl_center"] + torch.mean(centers_pred_o[:, 3:, :], -1)
+        if phase == "sil":
+            obj_losses, image, edges, image_ref, edt_ref = data_dict["silhouette"](R, obj_t, obj_s)
+            loss_dict["mask"] = obj_losses["mask"]
+            data_dict["image_ref"], data_dict["edt_ref"] = image_ref, edt_ref
+            loss_dict["scale"] = torch.mean((obj_s - self.obj_scale) ** 2)
+            loss_dict["trans"] = torch.mean((obj_t - data_dict["trans_init"]) ** 2)
+            return loss_dict
         self.compute_obj_loss(data_dict, loss_dict, model, obj_s, object)
         obj_center_act = torch.mean(object, 1)
         loss_dict["ocent"] = F.mse_loss(obj_center_act, obj_center_pred, reduction="none").sum(-1).mean()
+        if phase == "joint":
+            smpl_verts = smpl()[0]
+            df_obj_h = df_pred[:, 0, :]
+            with heads(model, _lib.HEAD_DF):
+                model.query(smpl_verts, **data_dict["query_dict"])
+            df_hum_o = model.get_preds()[0][:, 1, :]
+            self.compute_contact_loss(df_hum_o, df_obj_h, object, smpl_verts, loss_dict, part_o=part_o)
+            pen = self.compute_collision_loss(smpl_verts, smpl.faces, R, obj_t, obj_s)
+            if pen is not None:
+                loss_dict["collide"] = pen
         return loss_dict
 
     def forward_smpl(self, smpl, data_dict, phase="global"):
@@ -407,27 +478,52 @@ class ReconFitterBehave(ReconFitterBase):
         return self.copy_smpl_params(smpl_split, smpl), scale
 
     def optimize_smpl_object(self, model, data_dict, obj_iter=20, joint_iter=10, steps_per_iter=10,
-                             log: Optional[Callable[[str], None]] = None):
-        """recon_fit_behave.py:90-163, phase 'object only' (obj_iter x steps_per_iter Adam steps on
-        obj_t, obj_R, obj_s, lr 0.006, decay 1).  The 'sil' and 'joint' phases that follow in the reference
-        need the silhouette renderer and the contact / collision terms and are not run:
-        joint_iter is accepted for signature parity and ignored."""
+                             log: Optional[Callable[[str], None]] = None, sil_iter: int = 50, max_iter: int = 100):
+        """recon_fit_behave.py:90-163, the reference's schedule: `obj_iter` outer iterations 'object only' (Adam on obj_t, obj_R,
+        obj_s, lr 0.006, decay 1), then `sil_iter` (50) 'sil' iterations (a fresh Adam on obj_R, obj_s, obj_t; decay it - obj_iter + 1),
+        then 'joint' (a fresh Adam on obj_t, obj_s, lr 0.002; decay (it - obj_iter + 1) / 5) for joint_iter + max_iter iterations
+        with the reference's early-stop rule.  zero_grad() once per outer iteration (gradients accumulate over the inner steps).
+        The 'sil' phase runs when data_dict['silhouette'] holds a silhouette loss (chore_b200.silhouette.SilLossROI, built from
+        data_dict['images'] when a `scan` mesh was given to the fitter) and is skipped otherwise."""
         smpl = data_dict["smpl"]
         smpl_split = self.split_smpl(smpl)
         data_dict["smpl"] = smpl_split
         obj_R, obj_t, obj_s = data_dict["obj_R"], data_dict["obj_t"], data_dict["obj_s"]
+        if "silhouette" not in data_dict and getattr(self, "scan", None) is not None and "images" in data_dict:
+            from .silhouette import SilLossROI
+            images = data_dict["images"]
+            data_dict["silhouette"] = SilLossROI(images[:, 3, :, :], images[:, 4, :, :], self.scan, data_dict["query_dict"]["crop_center"],
+                                                 device=obj_t.device)
+        has_sil = "silhouette" in data_dict
+        iter_for_sil = sil_iter if has_sil else 0
         opt = torch.optim.Adam([obj_t, obj_R, obj_s], lr=0.006)
         weight_dict = self.get_loss_weights()
         data_dict["smpl_center"] = self.compute_smpl_center_pred(data_dict, model, smpl)
-        for it in range(obj_iter):
+        prev_loss = 300.0
+        phase = "object only"
+        for it in range(joint_iter + obj_iter + max_iter + iter_for_sil):
             opt.zero_grad()
+            if it == obj_iter and has_sil:
+                phase = "sil"
+                opt = torch.optim.Adam([obj_R, obj_s, obj_t], lr=0.006)
+                data_dict["rot_init"] = self.decopose_axis(obj_R).detach().clone()
+                data_dict["trans_init"] = obj_t.detach().clone()
+            if it == obj_iter + iter_for_sil:
+                phase = "joint"
+                opt = torch.optim.Adam([obj_t, obj_s], lr=0.002)
             for i in range(steps_per_iter):
-                loss_dict = self.forward_step(model, smpl_split, data_dict, obj_R, obj_t, obj_s, "object only")
-                loss = self.sum_dict(loss_dict, weight_dict, 1)
+                loss_dict = self.forward_step(model, smpl_split, data_dict, obj_R, obj_t, obj_s, phase)
+                decay = 1 if phase == "object only" else (it - obj_iter + 1 if phase == "sil" else (it - obj_iter + 1) / 5)
+                loss = self.sum_dict(loss_dict, weight_dict, decay)
                 loss.backward()
                 opt.step()
                 if log is not None:
-                    log("optimizing object only " + self.get_loss_str(f"{it}-{i}", loss_dict, weight_dict, 1))
+                    log(f"{phase} " + self.get_loss_str(f"{it}-{i}", loss_dict, weight_dict, decay))
+                if phase == "joint" and it > 0.25 * max_iter:       # early stop (:158-160): one host sync, only where it can fire
+                    lv, pv = float(loss.detach()), float(prev_loss)
+                    if abs(pv - lv) / pv < pv * 0.0001:
+                        return smpl, data_dict["obj_R"], data_dict["obj_t"]
+                prev_loss = loss.detach()
         return smpl, data_dict["obj_R"], data_dict["obj_t"]
 
 

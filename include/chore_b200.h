@@ -223,6 +223,18 @@ int chore_surface_clamp_grad(chore_handle *h, const float *df, int df_idx, float
 int chore_surface_step(chore_handle *h, const float *points, const float *g_points, const float *df, int df_idx,
                        float threshold, int B, int N, float *out_points, void *stream);
 
+/* ---- joint-phase contact term: ReconFitterBase.compute_contact_loss (recon/recon_fit_base.py:553-608): contact points =
+ *      cross distance field < thresh (0.08 m; all points of a side that has none), split by SMPL part (fixed vertex labels
+ *      `part_labels` (Nh), argmax of `part_o` (B,14,No) for the object points), one cloud pair per (image, part) present on
+ *      both sides, pytorch3d chamfer_distance defaults over the pairs (squared distances, mean per cloud, mean over pairs,
+ *      both directions).  loss: 1 float, n_pairs: 1 int32 (0 = "no contact": the reference adds no term);
+ *      g_smpl (B,Nh,3) / g_obj (B,No,3): d loss / d points, optional. ---------------------------------------------------- */
+size_t chore_contact_workspace_bytes(int B, int Nh, int No);
+int chore_contact_loss(chore_handle *h, const float *smpl_verts, const float *object, const float *df_hum_o,
+                       const float *df_obj_h, const float *part_o, const int32_t *part_labels, int B, int Nh, int No,
+                       float thresh, float *loss, int32_t *n_pairs, float *g_smpl, float *g_obj, void *workspace,
+                       size_t workspace_bytes, void *stream);
+
 /* ---- bookkeeping of Generator.gen_pc_batch (recon/generator.py:123-217) on the device: what the reference does with
  *      boolean indexing, Python lists and .cpu() / .item() round trips per image and outer iteration.  B images, N samples
  *      of this outer iteration; `cap` = capacity of the per-image output buffers. -------------------------------------- */

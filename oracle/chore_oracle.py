@@ -519,6 +519,42 @@ def smpl_losses(sd, feat, tmpx, crop_center, verts: Tensor, part_labels: Tensor)
 
 
 # ----------------------------------------------------------------------------------------
+# joint-phase contact term (recon/recon_fit_base.py:553-608)
+# ----------------------------------------------------------------------------------------
+def chamfer_distance_lists(xs: Sequence[Tensor], ys: Sequence[Tensor]) -> Tensor:
+    """pytorch3d.loss.chamfer_distance(Pointclouds(xs), Pointclouds(ys)) with its default arguments (point_reduction='mean',
+    batch_reduction='mean', norm=2): per pair mean_p min_q |x_p - y_q|^2 + mean_q min_p |x_p - y_q|^2, averaged over the pairs.
+    pytorch3d is not vendored by the reference (requirements.txt:22, unpinned git HEAD): this restates the documented default
+    (pytorch3d/loss/chamfer.py, releases 0.4 - 0.7) -- parity unpinned for this term."""
+    total = 0.0
+    for x, y in zip(xs, ys):
+        d = ((x[:, None, :] - y[None, :, :]) ** 2).sum(-1)
+        total = total + d.min(1).values.mean() + d.min(0).values.mean()
+    return total / len(xs)
+
+
+def contact_loss(df_hum_o: Tensor, df_obj_h: Tensor, obj: Tensor, smpl_verts: Tensor, part_o: Tensor, part_labels: Tensor,
+                 thresh: float = 0.08):
+    """ReconFitterBase.compute_contact_loss (recon_fit_base.py:553-608): None when no contact is found anywhere."""
+    pts_h, pts_o = [], []
+    po_all = torch.argmax(part_o, 1)
+    for hum, ob, mh, mo, po in zip(smpl_verts, obj, df_hum_o < thresh, df_obj_h < thresh, po_all):
+        ch, co = int(mh.sum()), int(mo.sum())
+        if ch + co == 0:
+            continue
+        obj_v, label_o = (ob[mo], po[mo]) if co > 0 else (ob, po)
+        hum_v, label_h = (hum[mh], part_labels[mh]) if ch > 0 else (hum, part_labels)
+        for i in range(14):
+            if not bool((label_h == i).any()) or not bool((label_o == i).any()):
+                continue
+            pts_h.append(hum_v[label_h == i])
+            pts_o.append(obj_v[label_o == i])
+    if not pts_o:
+        return None
+    return chamfer_distance_lists(pts_h, pts_o)
+
+
+# ----------------------------------------------------------------------------------------
 # full SMPL-phase step (recon/recon_fit_behave.py:293-337 with recon_fit_base.py:230-231,522-542,653-676)
 # ----------------------------------------------------------------------------------------
 def mahalanobis(pose: Tensor, mean: Tensor, prec: Tensor, prefix: int = 3, end: int = 66) -> Tensor:
