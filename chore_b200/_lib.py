@@ -64,6 +64,9 @@ SIGNATURES = {
     "chore_add_rowvec": (_I, [_P, _P, _P, _I, _I, _F, _P]),
     "chore_surface_clamp_grad": (_I, [_P, _P, _I, _F, _I, _I, _P, _P]),
     "chore_surface_step": (_I, [_P, _P, _P, _P, _I, _F, _I, _I, _P, _P]),
+    "chore_silhouette_workspace_bytes": (C.c_size_t, [_I, _I]),
+    "chore_silhouette_fwd": (_I, [_P, _P, _I, _I, _I, _F, _F, _P, _P, _P, C.c_size_t, _P]),
+    "chore_silhouette_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _P]),
     "chore_contact_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
     "chore_contact_loss": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "chore_gen_compact": (_I, [_P, _P, _I, _F, _F, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
@@ -358,6 +361,29 @@ class Handle:
             self._check(self.lib.chore_surface_step(self.h, points.data_ptr(), g_points.data_ptr(), df.data_ptr(), df_idx, threshold,
                                                     points.shape[0], points.shape[1], out.data_ptr(), _stream()))
         return out
+
+    # ---- silhouette rasteriser (csrc/silhouette.cu) ----------------------------------------------------
+    def silhouette_fwd(self, faces, image_size: int, near: float = 0.1, far: float = 100.0):
+        """faces (B,F,3,3) -> (alpha (B,S,S), face_index int32 (B,S,S)), rows not flipped."""
+        check_cuda(faces)
+        B, F = faces.shape[0], faces.shape[1]
+        alpha = torch.empty(B, image_size, image_size, device=faces.device)
+        index = torch.empty(B, image_size, image_size, dtype=torch.int32, device=faces.device)
+        nbytes = int(self.lib.chore_silhouette_workspace_bytes(B, F))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=faces.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.chore_silhouette_fwd(self.h, faces.data_ptr(), B, F, image_size, near, far, alpha.data_ptr(),
+                                                      index.data_ptr(), ws.data_ptr(), nbytes, _stream()))
+        return alpha, index
+
+    def silhouette_bwd(self, faces, face_index, alpha, g_alpha, eps: float = 1e-4):
+        check_cuda(faces, alpha, g_alpha)
+        B, F, S = faces.shape[0], faces.shape[1], alpha.shape[1]
+        g_faces = torch.empty_like(faces)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.chore_silhouette_bwd(self.h, faces.data_ptr(), face_index.data_ptr(), alpha.data_ptr(), g_alpha.data_ptr(),
+                                                      B, F, S, eps, g_faces.data_ptr(), _stream()))
+        return g_faces
 
     # ---- joint-phase contact term (csrc/contact.cu) ----------------------------------------------------
     def contact_loss(self, smpl_verts, obj, df_hum_o, df_obj_h, part_o, part_labels, thresh: float = 0.08, want_grads: bool = True):

@@ -182,11 +182,13 @@ class ReconFitterBase:
     """The kernel-backed subset of recon/recon_fit_base.py:ReconFitterBase."""
 
     def __init__(self, device="cuda:0", obj_scale: float = 1.0, debug: bool = False, priors=None,
-                 net_in_size: int = 512, crop_size: float = 1200.0, strict: bool = False):
+                 net_in_size: int = 512, crop_size: float = 1200.0, strict: bool = False, scan=None, part_labels=None):
         """priors: (MahalanobisPrior, HandPrior) from load_priors(), or None.  net_in_size / crop_size:
         args.net_img_size[0] / KinectColorCamera(args.loadSize).crop_size (recon_fit_base.py:74-75).
         strict: raise when forward_smpl lacks the priors / landmark regressors / data_dict entries its
-        non-field terms need (the reference always has them); otherwise those terms are left out."""
+        non-field terms need (the reference always has them); otherwise those terms are left out.
+        scan: the object template mesh (recon_fit_base.py:107-125 loads it from the BEHAVE object folder); part_labels:
+        load_part_labels(assets_root)."""
         self.device = device
         self.obj_scale = obj_scale
         self.debug = debug
@@ -199,6 +201,9 @@ class ReconFitterBase:
             # crop here would make the keypoint term and the field query disagree silently
             raise ValueError(f"chore_b200 is built for loadSize / crop_size 1200, got {crop_size}")
         self.strict = strict
+        self.scan = scan                    # centred object template (.v (V,3), .f (F,3)): silhouette phase, save_outputs
+        self.part_labels = part_labels      # (6890,) SMPL part index per vertex: contact term (load_part_labels)
+        self.collision_fn = None            # optional interpenetration term (see compute_collision_loss)
         # KinectColorCamera pixel intrinsics (model/camera.py:26-40)
         self.fx_px, self.fy_px = 979.7844 / 2048. * 2048, 979.840 / 2048. * 2048
         self.cx_px, self.cy_px = 1018.952 / 2048. * 2048, 779.486 / 2048. * 2048

@@ -223,6 +223,18 @@ int chore_surface_clamp_grad(chore_handle *h, const float *df, int df_idx, float
 int chore_surface_step(chore_handle *h, const float *points, const float *g_points, const float *df, int df_idx,
                        float threshold, int B, int N, float *out_points, void *stream);
 
+/* ---- silhouette rasteriser of the 'sil' fitting phase: replaces neural_renderer's rasterize_silhouettes as used by
+ *      SilLossROI.forward (recon/obj_pose_roi.py:159-172; external/neural_renderer/neural_renderer/cuda/
+ *      rasterize_cuda_kernel.cu:25-216 forward_face_index_map kernels, :291-550 backward_pixel_map kernel).
+ *      faces (B,F,3,3): per face 3 vertices (x, y in normalised image coordinates [-1,1], z = depth); image rows are NOT
+ *      flipped here (the reference flips after rasterising, rasterize.py:318-322).  alpha (B,S,S) in {0,1},
+ *      face_index (B,S,S) int32 (-1 = background); g_faces (B,F,3,3): only the x / y entries are non-zero. ------------ */
+size_t chore_silhouette_workspace_bytes(int B, int F);
+int chore_silhouette_fwd(chore_handle *h, const float *faces, int B, int F, int image_size, float near, float far,
+                         float *alpha, int32_t *face_index, void *workspace, size_t workspace_bytes, void *stream);
+int chore_silhouette_bwd(chore_handle *h, const float *faces, const int32_t *face_index, const float *alpha,
+                         const float *g_alpha, int B, int F, int image_size, float eps, float *g_faces, void *stream);
+
 /* ---- joint-phase contact term: ReconFitterBase.compute_contact_loss (recon/recon_fit_base.py:553-608): contact points =
  *      cross distance field < thresh (0.08 m; all points of a side that has none), split by SMPL part (fixed vertex labels
  *      `part_labels` (Nh), argmax of `part_o` (B,14,No) for the object points), one cloud pair per (image, part) present on

@@ -866,6 +866,21 @@ def test_optimize_loops_run_and_descend(net, smpl_layer):
     # unless the reference's early-stop rule fires
     assert out[0] is w and 6 < len(logs) <= 12 and "ocent" in logs[0] and logs[0].startswith("object only") and logs[6].startswith("joint")
     assert data["smpl_center"].shape == (2, 3) and not torch.equal(data["obj_t"].detach(), t0)
+    # with an object template and the network-input masks the 'sil' phase runs in between (recon_fit_behave.py:129-136)
+    import types
+    from test_silhouette_gpu import uv_sphere
+    v, f = uv_sphere(12, 16, 0.3)
+    fit.scan = types.SimpleNamespace(v=v, f=f)
+    yy, xx = torch.meshgrid(torch.arange(512.0), torch.arange(512.0), indexing="ij")
+    images = torch.zeros(2, 5, 512, 512)
+    images[:, 3] = ((xx - 230) ** 2 + (yy - 250) ** 2 < 60 ** 2).float()
+    images[:, 4] = ((xx - 300) ** 2 + (yy - 260) ** 2 < 70 ** 2).float()
+    data.pop("silhouette", None)
+    data["images"] = images.to(DEV)
+    logs = []
+    fit.optimize_smpl_object(net, data, obj_iter=1, joint_iter=1, steps_per_iter=2, max_iter=1, sil_iter=1, log=logs.append)
+    assert logs[0].startswith("object only") and logs[2].startswith("sil") and "mask" in logs[2] and "trans" in logs[2]
+    assert logs[4].startswith("joint") and "rot_init" in data and data["silhouette"].image_ref.shape == (2, 256, 256)
 
 
 def test_contact_loss_vs_oracle():
