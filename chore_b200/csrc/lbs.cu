@@ -445,7 +445,9 @@ __device__ void so3_decompose(const float *__restrict__ mat, So3 &o) {
     // cyclic Jacobi on the symmetric S = M^T M
     for (int sweep = 0; sweep < 30; ++sweep) {
         const double off = fabs(S[0][1]) + fabs(S[0][2]) + fabs(S[1][2]);
-        if (off < 1e-300) break;
+        // converged to fp64 round-off relative to the spectrum (Jacobi converges quadratically: 5-6 sweeps); the result is
+        // rounded to fp32 afterwards.  Sweeping on to an exact zero cost 30 sweeps = 40 us of a 480 us fit iteration.
+        if (off <= 1e-17 * (fabs(S[0][0]) + fabs(S[1][1]) + fabs(S[2][2])) || off < 1e-300) break;
         for (int pq = 0; pq < 3; ++pq) {
             const int pi = pq == 2 ? 1 : 0, qi = pq == 0 ? 1 : 2;
             if (fabs(S[pi][qi]) < 1e-300) continue;

@@ -632,6 +632,7 @@ class FusedFitSteps:
         self.cc = data_dict["query_dict"]["crop_center"].detach().float().contiguous()
         nmax = max(smpl.offsets.shape[1], data_dict["objects"].shape[1]) if "objects" in data_dict else smpl.offsets.shape[1]
         self.ws = self.h_aux.fit_workspace(obj_t.shape[0], nmax, dev)
+        self.ws_obj = self.h_aux.fit_workspace(obj_t.shape[0], nmax, dev)      # own scratch: the two steps may run concurrently
         self.loss_smpl = torch.zeros(1, device=dev)
         self.loss_obj = torch.zeros(1, device=dev)
         self.priors_dev = None
@@ -722,7 +723,7 @@ class FusedFitSteps:
         k = 1.0          # see smpl_step
         wc = self.W["ocent"] * k / B
         g_df, g_cen, dvec = self.h_aux.fit_obj_field_grads(obj, df, cen, d["smpl_center"], s, self.obj_scale, self.W["object"] * k / (B * N), wc,
-                                                           self.W["scale"] * k / B, loss, self.ws)
+                                                           self.W["scale"] * k / B, loss, self.ws_obj)
         g_obj = self.h_net.query_bwd(feat, skip, obj, self.cc, [g_df, None, None, g_cen])
         self.h_aux.add_rowvec(g_obj, dvec, 2.0 * wc / N)
         g_R, g_t, g_s, _ = self.h_aux.rigid_bwd(obj0, Rm, t, s, g_obj, False)
@@ -731,6 +732,27 @@ class FusedFitSteps:
         self._g_obj = (g_t, g_rot, g_s)
         self.opt_obj.step(self._g_obj, self.kdev, loss)
         return loss
+
+    def iteration(self, noise: Optional[torch.Tensor] = None):
+        """One fit iteration = SMPL step + 'object only' step.  The two touch disjoint parameters and scratch (the object step
+        reads the SMPL centre computed once before the loop, recon_fit_behave.py:112), so the object step is forked onto a side
+        stream and joined at the end: their many single-block kernels (kinematic chain, SO(3), Adam, reductions) overlap with the
+        other step's field queries.  Capturable: `graphed_iteration()`."""
+        cur = torch.cuda.current_stream()
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.t.device)
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            lo = self.object_step(noise)
+        ls = self.smpl_step()
+        cur.wait_stream(self._side)
+        return ls, lo
+
+    def graphed_iteration(self):
+        """`iteration()` captured in ONE CUDA graph (fork / join inside); warm-up undone like `graphed()`."""
+        snap = lambda: (self.opt_smpl.state(), self.opt_obj.state(), self.loss_smpl.clone(), self.loss_obj.clone())
+        rest = lambda st: (self.opt_smpl.load_state(st[0]), self.opt_obj.load_state(st[1]), self.loss_smpl.copy_(st[2]), self.loss_obj.copy_(st[3]))
+        return GraphedStep(self.iteration, snapshot=snap, restore=rest)
 
     def graphed(self):
         """(smpl_step, object_step) of the CURRENT phase captured in CUDA graphs; each call replays one optimisation

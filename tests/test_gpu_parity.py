@@ -654,6 +654,43 @@ def test_fused_fit_loop_matches_reference_loop_semantics(net, smpl_layer):
     assert rel_err(0.5 * fh._g_pose_full[:, 66:], sh.hand_pose.grad) < 1e-4, rel_err(0.5 * fh._g_pose_full[:, 66:], sh.hand_pose.grad)
 
 
+def test_fused_iteration_two_streams_equals_sequential(net, smpl_layer):
+    """FusedFitSteps.iteration() (object step forked onto a side stream, joined) and its captured form give the same first update as
+    the two steps run one after the other: the steps touch disjoint parameters and scratch."""
+    import chore_b200
+    g = load_golden("fit_smpl_full.npz")
+    fit, w, data, _ = _smpl_full_setup(net, smpl_layer, g)
+    gen = torch.Generator().manual_seed(29)
+    data.update({"objects": (0.2 * torch.randn(2, 4000, 3, generator=gen)).to(DEV),
+                 "smpl_center": torch.tensor([[0.0, 0.1, 2.2], [0.0, 0.0, 2.2]], device=DEV)})
+    noise = torch.rand(2, 3, 3, generator=gen).to(DEV)
+    mkobj = lambda: ((torch.eye(3).repeat(2, 1, 1) + 0.05 * torch.randn(2, 3, 3, generator=torch.Generator().manual_seed(3))).to(DEV).requires_grad_(True),
+                     torch.tensor([[0.2, 0.1, 2.3], [0.1, 0.0, 2.2]], device=DEV, requires_grad=True), torch.ones(2, device=DEV, requires_grad=True))
+
+    def run(mode):
+        sf = fit.split_smpl(w); R, t, s = mkobj()
+        fused = chore_b200.FusedFitSteps(net, sf, data, R, t, s, fitter=fit, phase="kpts")
+        fused.zero_grad()
+        if mode == "seq":
+            fused.smpl_step(); fused.object_step(noise)
+        elif mode == "fork":
+            fused.iteration(noise)
+        else:
+            step = fused.graphed_iteration()         # draws its own noise on the device: compare the SMPL side + counters only
+            step()
+        torch.cuda.synchronize()
+        return fused, sf, (R, t, s)
+
+    f0, s0, o0 = run("seq")
+    f1, s1, o1 = run("fork")
+    f2, s2, o2 = run("graph")
+    for n in ("trans", "global_pose", "body_pose", "top_betas", "other_betas"):
+        assert (getattr(s0, n) - getattr(s1, n)).abs().max() < 1e-6 and (getattr(s0, n) - getattr(s2, n)).abs().max() < 1e-6, n
+    for a, b in zip(o0, o1):
+        assert (a - b).abs().max() < 1e-6
+    assert int(f2.opt_smpl.step_count) == 1 and int(f2.opt_obj.step_count) == 1 and not torch.equal(o2[1], mkobj()[1])
+
+
 def test_generator_device_kernels(net):
     """csrc/generator.cu against torch: ordered compaction == boolean-mask indexing, resampling == the reference's formula for
     given draws, Philox draws reproducible and in range, finalize == mean over the kept prefix."""
