@@ -35,9 +35,11 @@ constexpr int kThreadsHx = (kFirstTxWarp + kTxWarps) * 32;   // 448
 constexpr int kMaxSlots = 8;
 constexpr uint32_t kSmemBudget = 232448;               // 227 KB opt-in maximum per CTA
 constexpr uint32_t kStagePitch = 144, kStageWarpBytes = 32 * kStagePitch;   // epilogue transpose tile (padded rows: conflict free)
+constexpr uint32_t kRecvOff = 40960;                   // K split: received partial chunks start here (after the helpers' staging tiles)
 
 struct HxCtl {
     uint64_t halo_full[2], halo_empty[2], w_full[kMaxSlots], w_empty[kMaxSlots], acc_full[2], acc_empty[2];
+    uint64_t peer_ready[8], data_full, pad64;                 // K split: cluster partner r can receive / all partials of my chunks landed
     uint32_t tmem_base, pad[3];
     uint2 dummy[4];                                    // target of the stores of halo slots beyond the tile
     float sc[256], sh[256];
@@ -49,8 +51,6 @@ struct HxParams {
     int n_splits, k_splits, kt_per, Ns, tiles_x, tiles_y, n_items, kblocks, n_slots;
     uint32_t halo_plane, w_slot;
     double inv_n;          // 1 / (H * W * channels per group of the input)
-    float *part;           // K split: [(tile, n slice)][k_splits][128][Ns] fp32 partial tiles (a part parks the chunks it does not own)
-    int *part_cnt;         // K split: arrivals per (tile, n slice), zeroed before the launch
     long long *trace;      // debugging: 32 clock64 stamps of CTA 0 (null = off)
 };
 
@@ -168,6 +168,16 @@ __global__ void __launch_bounds__(kThreadsHx, 1) conv_hx_kernel(const HxParams p
             mbar_init(&ctl->acc_full[i], 1); mbar_init(&ctl->acc_empty[i], 4);
         }
         for (int i = 0; i < kMaxSlots; ++i) { mbar_init(&ctl->w_full[i], 1); mbar_init(&ctl->w_empty[i], 1); }
+        if (p.k_splits > 1) {
+            // K split: the parts of one (tile, n slice) form a thread-block cluster (rank = K part) and exchange their
+            // partial accumulators through distributed shared memory
+            const int me = (int)(blockIdx.x % p.k_splits), n_chunks = p.Ns / 32;
+            const int owned = n_chunks > me ? (n_chunks - me + p.k_splits - 1) / p.k_splits : 0;
+            for (int i = 0; i < 8; ++i) mbar_init(&ctl->peer_ready[i], 1);
+            mbar_init(&ctl->data_full, 1);
+            // the senders' st.async stores complete the transaction count: (k_splits - 1) partials of every owned chunk
+            if (owned > 0) mbar_arrive_expect_tx(&ctl->data_full, (uint32_t)((p.k_splits - 1) * owned) * 16384u);
+        }
         fence_barrier_init();
     }
     for (int i = threadIdx.x; i < 12 * 2 * kGroups * 2; i += kThreadsHx) (&ctl->stp[0][0][0])[i] = 0.f;
@@ -185,6 +195,8 @@ __global__ void __launch_bounds__(kThreadsHx, 1) conv_hx_kernel(const HxParams p
     }
     tc_fence_before();
     __syncthreads();
+    // the partners' barriers must exist before anybody signals them: arrive now, wait right before the first remote access
+    if (p.k_splits > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");   // (fence.mbarrier_init released them)
     tc_fence_after();
     const uint32_t tmem_base = ctl->tmem_base;
     if (warp == 0) HX_STAMP(1);
@@ -301,6 +313,7 @@ __global__ void __launch_bounds__(kThreadsHx, 1) conv_hx_kernel(const HxParams p
                 okm |= (off[j] >= 0 ? 1u : 0u) << j;
             }
         }
+        if (warp == kFirstTxWarp) HX_STAMP(12);
         while (item < p.n_items) {
             if (b_item != cur_b) {
                 if (cur_b >= 0) {                                 // nobody still reads the previous image's table
@@ -322,6 +335,7 @@ __global__ void __launch_bounds__(kThreadsHx, 1) conv_hx_kernel(const HxParams p
                     }
                     ctl->sc[t] = sc; ctl->sh[t] = sh;
                 }
+                if (cur_b < 0 && warp == kFirstTxWarp) HX_STAMP(13);
                 named_bar(2, kTxWarps * 32);
                 if (cur_b < 0 && warp == kFirstTxWarp) HX_STAMP(2);
                 cur_b = b_item;
@@ -347,6 +361,7 @@ __global__ void __launch_bounds__(kThreadsHx, 1) conv_hx_kernel(const HxParams p
                 }
                 const bool nc_ok = more && nkb * 64 + q * 4 < a.Cin;
                 mbar_wait(&ctl->halo_empty[hs], ((hc >> 1) & 1u) ^ 1u);
+                if (hc == 0 && warp == kFirstTxWarp) HX_STAMP(14);
                 const uint32_t hi_s = halo_s + hs * halo_stage + st_off;
 #pragma unroll
                 for (int j = 0; j < kSlots; ++j) {
@@ -440,33 +455,34 @@ __global__ void __launch_bounds__(kThreadsHx, 1) conv_hx_kernel(const HxParams p
             mbar_wait(&ctl->acc_full[abuf], (ic >> 1) & 1u);
             tc_fence_after();
             if (ic == 0 && warp == kFirstEpiWarp) HX_STAMP(16);
-            const size_t prow = (size_t)(quarter * 32 + rsub) * p.Ns + cq;   // this lane's first row / quad inside a partial tile
+            // K split exchange.  Every part is a receiver for the chunks it owns and a sender for the others.  A receiver
+            // announces that its own MMAs are complete (its halo buffers and weight ring are idle from then on); senders
+            // then push their transposed partial chunks straight into that idle shared memory of the owner (DSMEM stores)
+            // and arrive on the owner's data_full barrier; the owner adds the partials from its own shared memory.
+            const uint32_t recv0 = smem_u32(halo) + kRecvOff + (uint32_t)rsub * 128u + (uint32_t)(lane & 7) * 16u;
+            const int owned_max = (n_chunks + p.k_splits - 1) / p.k_splits;
             if (p.k_splits > 1) {
-                // park the chunks other parts own in the L2-resident scratch, signal, wait for everybody
-                float *mine = p.part + (size_t)(tn * p.k_splits + ks) * 128 * p.Ns + prow;
+                asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+                if (warp == kFirstEpiWarp && lane < p.k_splits && lane != ks && ks < n_chunks)
+                    mbar_arrive_remote(mapa(smem_u32(&ctl->peer_ready[ks]), (uint32_t)lane));
                 int parked = 0;
                 for (int ci = 0; ci < n_chunks; ++ci) {
-                    if (ci % p.k_splits == ks) continue;
+                    const int owner = ci % p.k_splits;
+                    if (owner == ks) continue;
                     if ((parked++) % workers != wslot) continue;
                     float4 x[8];
                     load_chunk(ci * 32, x);
+                    mbar_wait_cluster(&ctl->peer_ready[owner], 0);
+                    const int sidx = ks < owner ? ks : ks - 1;
+                    const uint32_t dst = mapa(recv0 + (uint32_t)(((sidx * owned_max + ci / p.k_splits) * 4 + quarter) * 4096), (uint32_t)owner);
+                    const uint32_t bar = mapa(smem_u32(&ctl->data_full), (uint32_t)owner);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) __stcg(reinterpret_cast<float4 *>(mine + (size_t)(4 * i) * p.Ns + ci * 32), x[i]);
+                    for (int i = 0; i < 8; ++i)
+                        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+                                     ::"r"(dst + i * 512), "f"(x[i].x), "f"(x[i].y), "f"(x[i].z), "f"(x[i].w), "r"(bar) : "memory");
                 }
-                __syncwarp();                               // the release below is cumulative over the warp's stores
-                if (lane == 0) {
-                    asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p.part_cnt + tn) : "memory");
-                    if (c_first < p.Ns) {                   // bounded wait: a lost arrival must not hang the GPU
-                        const int want = 4 * workers * p.k_splits;
-                        int got = 0;
-                        for (int spin = 0; spin < (1 << 24); ++spin) {
-                            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(got) : "l"(p.part_cnt + tn) : "memory");
-                            if (got >= want) break;
-                        }
-                    }
-                }
-                __syncwarp();
                 if (ic == 0 && warp == kFirstEpiWarp) HX_STAMP(19);
+                if (c_first < p.Ns) mbar_wait_cluster(&ctl->data_full, 0);
             }
             for (int c0 = c_first; c0 < p.Ns; c0 += c_step) {
                 float4 x[8];
@@ -474,12 +490,13 @@ __global__ void __launch_bounds__(kThreadsHx, 1) conv_hx_kernel(const HxParams p
                 const int c = n0 + c0 + cq;                  // absolute first channel of this lane's quad
                 const bool stamp = ic == 0 && c0 == c_first && warp == kFirstEpiWarp;
                 if (stamp) HX_STAMP(20);
-                for (int k2 = 0; k2 < p.k_splits; ++k2) {
-                    if (k2 == ks) continue;
-                    const float *pk = p.part + (size_t)(tn * p.k_splits + k2) * 128 * p.Ns + prow + c0;
+                for (int k2 = 0; k2 < p.k_splits - 1; ++k2) {       // partials in sender order: deterministic sums
+                    const uint32_t src = recv0 + (uint32_t)(((k2 * owned_max + (c0 >> 5) / p.k_splits) * 4 + quarter) * 4096);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const float4 pv = __ldcg(reinterpret_cast<const float4 *>(pk + (size_t)(4 * i) * p.Ns));
+                        float4 pv;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(pv.x), "=f"(pv.y), "=f"(pv.z), "=f"(pv.w)
+                                     : "r"(src + i * 512) : "memory");
                         x[i].x += pv.x; x[i].y += pv.y; x[i].z += pv.z; x[i].w += pv.w;
                     }
                 }
@@ -533,6 +550,9 @@ __global__ void __launch_bounds__(kThreadsHx, 1) conv_hx_kernel(const HxParams p
     }
     tc_fence_before();
     __syncthreads();
+    // K split: every remote arrival on and every store into this CTA has been waited for above (each part sends to and
+    // hears from every owner), so no closing cluster barrier is needed; warps 0 / 1 complete the opening one here
+    if (p.k_splits > 1 && warp < 2) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     if (warp == 0) HX_STAMP(24);
     if (warp == 1) {
         tc_fence_after();
@@ -613,8 +633,8 @@ int conv_hx_plan(const chore_handle *h, const ConvHxArgs &a, ConvHxPlan *pl) {
     int ns = 1;
     while (tiles * ks * ns * 2 <= h->sm_count && a.N / (ns * 2) >= 32) ns *= 2;
     pl->tiles = tiles; pl->k_splits = ks; pl->n_splits = ns;
-    pl->part_floats = ks > 1 ? (size_t)tiles * ns * ks * 128 * (a.N / ns) : 0;
-    pl->counters = ks > 1 ? tiles * ns : 0;
+    pl->part_floats = 0;                                   // the K parts exchange through distributed shared memory
+    pl->counters = 0;
     return CHORE_OK;
 }
 
@@ -622,8 +642,9 @@ int conv_hx_launch(chore_handle *h, const ConvHxArgs &a, const ConvHxPlan &pl, f
     CHORE_CHECK((a.ld_in | a.off_in | a.ld_out | a.off_out | a.ld_res | a.off_res | a.ld_raw | a.off_raw) % 4 == 0, "conv_hx: unaligned channel offsets");
     CHORE_CHECK((!a.st_raw || (a.cpg_raw >= 1 && a.cpg_raw <= 8 && (a.cpg_raw & (a.cpg_raw - 1)) == 0)) &&
                 (!a.st_out || (a.cpg_out >= 1 && a.cpg_out <= 8 && (a.cpg_out & (a.cpg_out - 1)) == 0)), "conv_hx: group width");
-    CHORE_CHECK(pl.k_splits == 1 || (part != nullptr && part_cnt != nullptr && pl.tiles * pl.n_splits * pl.k_splits <= h->sm_count),
-                "conv_hx: K split needs scratch and co-resident parts");
+    (void)part; (void)part_cnt;
+    CHORE_CHECK(pl.k_splits >= 1 && pl.k_splits <= 8 && (pl.k_splits == 1 || pl.tiles * pl.n_splits * pl.k_splits <= h->sm_count),
+                "conv_hx: K split of %d parts", pl.k_splits);
     if (int rc = conv_hx_configure(h)) return rc;
     HxParams p{};
     p.a = a;
@@ -638,8 +659,6 @@ int conv_hx_launch(chore_handle *h, const ConvHxArgs &a, const ConvHxPlan &pl, f
     p.halo_plane = (uint32_t)(((kTileH + a.KS - 1) * (kTileW + a.KS - 1) * 128 + 1023) / 1024 * 1024);
     p.w_slot = (uint32_t)p.Ns * 256u;
     p.inv_n = 1.0 / ((double)a.H * a.W * (a.Cin / kGroups));
-    p.part = part;
-    p.part_cnt = part_cnt;
     const uint32_t fixed = 1024u + 4u * p.halo_plane + 4u * kStageWarpBytes + (uint32_t)sizeof(HxCtl);
     int slots = (int)((kSmemBudget - fixed) / p.w_slot);
     p.n_slots = slots > kMaxSlots ? kMaxSlots : slots;
@@ -647,6 +666,21 @@ int conv_hx_launch(chore_handle *h, const ConvHxArgs &a, const ConvHxPlan &pl, f
     const size_t smem = fixed + (size_t)p.n_slots * p.w_slot;
     const int grid = p.n_items < h->sm_count ? p.n_items : h->sm_count;
     p.trace = (g_hx_trace != nullptr && g_hx_trace_idx < 256) ? g_hx_trace + 32 * (g_hx_trace_idx++) : nullptr;
+    if (pl.k_splits > 1) {
+        // one cluster per (tile, n slice): rank = K part; the received partials live in the halo buffers + weight ring
+        const int n_chunks = p.Ns / 32, owned_max = (n_chunks + pl.k_splits - 1) / pl.k_splits;
+        const size_t need = kRecvOff + (size_t)(pl.k_splits - 1) * owned_max * 4 * 4096;
+        CHORE_CHECK(need <= 4 * (size_t)p.halo_plane + (size_t)p.n_slots * p.w_slot && grid == p.n_items, "conv_hx: K split exchange does not fit");
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreadsHx); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)pl.k_splits; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        if (a.KS == 3) CHORE_CUDA(cudaLaunchKernelEx(&cfg, conv_hx_kernel<3>, p));
+        else CHORE_CUDA(cudaLaunchKernelEx(&cfg, conv_hx_kernel<1>, p));
+        return CHORE_OK;
+    }
     if (a.KS == 3) CHORE_LAUNCH_PDL(conv_hx_kernel<3>, dim3(grid), dim3(kThreadsHx), smem, st, p);
     else CHORE_LAUNCH_PDL(conv_hx_kernel<1>, dim3(grid), dim3(kThreadsHx), smem, st, p);
     return CHORE_OK;

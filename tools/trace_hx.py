@@ -22,7 +22,7 @@ h.encode(img)
 torch.cuda.synchronize()
 lib.chore_debug_hx_trace(None)
 t = buf.view(256, 32).cpu()
-names = {0: "start", 1: "setup", 2: "table", 3: "tx0", 4: "tx1", 5: "tx2", 6: "tx3", 8: "mma0", 9: "mma1", 10: "mma2", 11: "mma3",
+names = {0: "start", 1: "setup", 12: "ld_issued", 13: "scsh", 2: "table", 14: "tx_go", 3: "tx0", 4: "tx1", 5: "tx2", 6: "tx3", 8: "mma0", 9: "mma1", 10: "mma2", 11: "mma3",
          16: "accfull", 19: "parts", 20: "c0_ld", 21: "c0_raw", 22: "c0_straw", 23: "c0_out", 25: "c0_stout", 17: "epi", 18: "flush", 24: "end"}
 for i in range(256):
     r = t[i]
