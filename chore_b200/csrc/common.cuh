@@ -145,10 +145,20 @@ struct LandmarkModel {
     bool loaded = false;
 };
 
+// dense-grid query with layer 1 folded into the feature maps (query_g.cu)
+struct QueryGWeights {
+    unsigned char *wf[2] = {nullptr, nullptr};   // conv_hx 1x1 weights: W1[:, 0:256] rows of heads {0,1} / {2,3}
+    unsigned char *ws[2] = {nullptr, nullptr};   // same for the 64 stem-skip channels W1[:, 259:323]
+    float *wz = nullptr;                         // [3][512] columns of x, y, z - 2.2
+    float *gf = nullptr, *gs = nullptr;          // projected maps of ONE image: [fh*fw][512], [4*fh*fw][512]
+    size_t map_px = 0;                           // fh*fw the maps were allocated for
+};
+
 struct chore_handle {
     int device = 0;
     int sm_count = 148;
     MlpWeights mlp;
+    QueryGWeights qg;
     EncoderWeights enc;
     LbsModel lbs;
     LandmarkModel lmk;
@@ -183,6 +193,12 @@ int query_bwd_tc_launch(chore_handle *h, const float *feat, const float *skip, i
                         const float *crop_center, int B, long long N, const float *const g_heads[4], float *g_points,
                         void *workspace, size_t workspace_bytes, cudaStream_t st);
 bool query_use_tensor_cores();   // CHORE_B200_QUERY=simt selects the fp32 SIMT kernel
+// dense-grid forward through per-pixel projected maps (query_g.cu); experimental, opt-in with CHORE_B200_QUERY_PRE=1
+int query_g_pack_weights(chore_handle *h, const std::vector<float> &w1);
+int query_g_mode();
+int query_g_launch(chore_handle *h, const float *feat, const float *skip, int fh, int fw, const float *crop_center, long long N,
+                   long long n_start, long long n_count, int batch_index, const int *res, const double *step, const double *bmin,
+                   unsigned head_mask, float *const outs[4], cudaStream_t st);
 // cta_group::2 forward for all four heads (query_tc2.cu); experimental, opt-in with CHORE_B200_QUERY_2CTA=1
 bool query_tc2_enabled();
 int query_tc2_launch(chore_handle *h, const float *feat, const float *skip, int fh, int fw, const float *points,

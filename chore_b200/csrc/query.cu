@@ -618,6 +618,7 @@ int query_load_weights(chore_handle *h, const std::map<std::string, const chore_
     rc |= upload(h, &m.w4, w4); rc |= upload(h, &m.b4, b4);
     if (rc) return CHORE_ERR_CUDA;
     if (int rc2 = query_tc_pack_weights(h, raw1, raw2, raw3, w4)) return rc2;
+    if (int rc2 = query_g_pack_weights(h, raw1)) return rc2;
     m.loaded = true;
     return CHORE_OK;
 }
@@ -696,6 +697,11 @@ extern "C" int chore_query_grid(chore_handle *h, const float *feat, const float 
     for (int i = 0; i < kNumHeads; ++i) q.out[i] = outs[i] ? outs[i] - (size_t)b * kHeadOut[i] * total : nullptr;
     q.in_img = nullptr;
     fill_weights(q, h->mlp);
+    if (query_use_tensor_cores()) {
+        if (query_g_mode() == 1)
+            return query_g_launch(h, feat, skip, fh, fw, crop_center, total, start, count, b, res, q.step, q.bmin, head_mask, q.out,
+                                  static_cast<cudaStream_t>(stream));
+    }
     if (query_use_tensor_cores() && head_mask == CHORE_HEAD_ALL && query_tc2_enabled())
         return query_tc2_launch(h, feat, skip, fh, fw, nullptr, crop_center, 1, total, start, count, 1, b, res, q.step, q.bmin, q.out, nullptr,
                                 static_cast<cudaStream_t>(stream));

@@ -1025,6 +1025,50 @@ def test_query_bwd_concurrent_heads_equal_sequential(net):
         assert torch.equal(seq, con), (k, (seq - con).abs().max().item())
 
 
+def test_projected_map_grid_query_matches_per_point_kernel(net, sd, monkeypatch):
+    """query_g.cu (opt-in, CHORE_B200_QUERY_PRE=1): layer 1 applied once per pixel (W1 . feat, W1 . skip as 1x1 convolutions on the
+    encoder's tensor-core kernel), then bilinear taps of the projected maps.  Same function as model/chore.py:107-167 up to
+    the order of fp32 additions: compared with the oracle and with the per-point kernel for every kind of head mask, ragged
+    ranges and both issuer layouts."""
+    feat, tmpx = O.synth_features(5, B=2)
+    set_maps(net, feat, tmpx)
+    f, s = net._maps()
+    cc = torch.tensor([[1008., 995.], [990., 1001.]], device=DEV)
+    pmin, pmax = (-3.0, -0.9, 0.2), (3.0, 1.8, 4.0)
+
+    def run(flag, res, start, count, mask, b=1):
+        monkeypatch.setenv("CHORE_B200_QUERY_PRE", flag)
+        total = res[0] * res[1] * res[2]
+        o = [torch.zeros(c, total, device=DEV) if (mask >> i) & 1 else None for i, c in enumerate((2, 9, 14, 6))]
+        net.handle.query_grid(f, s, cc, b, list(res), list(pmin), list(pmax), start, count, mask, o)
+        torch.cuda.synchronize()
+        return o
+
+    worst = 0.0
+    for issuers in ("2", "1"):
+        monkeypatch.setenv("CHORE_B200_QUERY_PRE_ISSUERS", issuers)
+        for res, start, cnt, mask in [((48, 40, 64), 0, 48 * 40 * 64, 15), ((48, 40, 64), 100, 48 * 40 * 64 - 137, 15),
+                                      ((40, 36, 50), 0, 72000, 1), ((40, 36, 50), 7, 71991, 13), ((40, 36, 50), 0, 72000, 10),
+                                      ((40, 36, 50), 0, 72000, 14), ((24, 20, 28), 0, 13440, 8), ((5, 4, 3), 0, 60, 15)]:
+            ref = run("0", res, start, cnt, mask)
+            got = run("1", res, start, cnt, mask)
+            for a, b in zip(got, ref):
+                if a is not None:
+                    e = rel_err(a, b)
+                    worst = max(worst, e)
+                    assert e < 2e-5, (issuers, res, start, cnt, mask, e)
+                    assert torch.equal(a[:, :start], b[:, :start]) and torch.equal(a[:, start + cnt:], b[:, start + cnt:])   # untouched outside the range
+    # and against the oracle itself
+    res = (12, 10, 9)
+    coords = torch.from_numpy(O.create_grid(res, list(pmin), list(pmax)).T.astype(np.float32)).unsqueeze(0)
+    with torch.no_grad():
+        ref = O.query(sd, feat[1:2], tmpx[1:2], coords, cc[1:2].cpu())
+    got = run("1", res, 0, res[0] * res[1] * res[2], 15)
+    for a, b in zip(got, ref[:4]):
+        assert rel_err(a, b.reshape(a.shape)) < TOL
+    report("projected_map_grid_query", worst_vs_per_point_kernel=worst)
+
+
 def test_cta_pair_kernel_is_bit_identical(net, monkeypatch):
     """query_tc2_kernel (tcgen05 cta_group::2: two CTAs of a cluster share every weight panel, layer 1 as N = 256 MMAs; opt-in
     with CHORE_B200_QUERY_2CTA=1) must reproduce query_tc_kernel bit for bit: same operands, same accumulation order.  Covers an
