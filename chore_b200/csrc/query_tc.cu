@@ -31,10 +31,15 @@
 
 namespace {
 
+// w_full / act_full exist once per issuer.  A parity wait is only meaningful for a waiter that is at most one phase ahead
+// of the barrier; on ONE barrier per ring slot, the issuer whose turn on a slot comes second tests a phase that is two ahead
+// and passes before the first issuer's panel has landed (seen as size-dependent hangs for the three-head masks 7 / 11 /
+// 13 / 14, where the issuers do not alternate slot by slot).  Producers therefore arrive on the barrier of the issuer that
+// owns the head, and every issuer tracks the parity of its own uses.  (a_full is waited on by both issuers for every block.)
 struct Bars {
     uint64_t a_full[kNA], a_empty[kNA];
-    uint64_t w_full[kNW], w_empty[kNW];
-    uint64_t act_full[kNACT], act_empty[kNACT];
+    uint64_t w_full[2][kNW], w_empty[kNW];
+    uint64_t act_full[2][kNACT], act_empty[kNACT];
     uint64_t tm_full[4], tm_empty[4];
     uint32_t tmem_base;
 };
@@ -64,15 +69,13 @@ __global__ void __launch_bounds__(kThreadsFwd, 1) query_tc_kernel(const TcParams
     const long long dbg_t0 = clock64();
 #define DBG(i) (dbg_on ? &dbg_local[i] : nullptr)
 
+    const unsigned owner_mask = 10u;             // heads whose steps the second issuer (warp 14) runs
     if (threadIdx.x == 0) {
-        // an A stage is released by every issuer that reads it.  Three active heads run on ONE issuer: with two issuers sharing the
-        // weight ring in global panel order, a 2 + 1 split of the heads can deadlock (issuer A waits for a ring slot that holds a panel
-        // of issuer B, B waits for the epilogue, the epilogue for an accumulator of A) -- seen as size-dependent hangs for masks
-        // 7 / 11 / 13 / 14; the 2 + 2 and 1 + 1 alternations are symmetric and never build that cycle.
-        const int n_issuers = __popc(q.head_mask) == 3 ? 1 : ((q.head_mask & 5u) != 0) + ((q.head_mask & 10u) != 0);
+        // an A stage is released by every issuer that reads it
+        const int n_issuers = ((q.head_mask & ~owner_mask) != 0) + ((q.head_mask & owner_mask) != 0);
         for (int i = 0; i < kNA; ++i) { mbar_init(&bars->a_full[i], 4); mbar_init(&bars->a_empty[i], n_issuers); }
-        for (int i = 0; i < kNW; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
-        for (int i = 0; i < kNACT; ++i) { mbar_init(&bars->act_full[i], 4); mbar_init(&bars->act_empty[i], 1); }
+        for (int i = 0; i < kNW; ++i) { mbar_init(&bars->w_full[0][i], 1); mbar_init(&bars->w_full[1][i], 1); mbar_init(&bars->w_empty[i], 1); }
+        for (int i = 0; i < kNACT; ++i) { mbar_init(&bars->act_full[0][i], 4); mbar_init(&bars->act_full[1][i], 4); mbar_init(&bars->act_empty[i], 1); }
         for (int i = 0; i < 4; ++i) { mbar_init(&bars->tm_full[i], 1); mbar_init(&bars->tm_empty[i], 4); }
         fence_barrier_init();
     }
@@ -103,8 +106,9 @@ __global__ void __launch_bounds__(kThreadsFwd, 1) query_tc_kernel(const TcParams
                     const uint32_t bytes = i < kBigUnits ? kPanelBytes : kSmallPanelBytes;
                     const size_t off = i < kBigUnits ? (size_t)i * kPanelBytes
                                                      : (size_t)kBigUnits * kPanelBytes + (size_t)(i - kBigUnits) * kSmallPanelBytes;
-                    mbar_arrive_expect_tx(&bars->w_full[s], bytes);
-                    bulk_g2s(ringW + (size_t)s * kPanelBytes, q.wstream + off, bytes, &bars->w_full[s]);
+                    uint64_t *full = &bars->w_full[(owner_mask >> hd_i) & 1][s];
+                    mbar_arrive_expect_tx(full, bytes);
+                    bulk_g2s(ringW + (size_t)s * kPanelBytes, q.wstream + off, bytes, full);
                 }
                 __syncwarp();
                 ++u;
@@ -116,7 +120,9 @@ __global__ void __launch_bounds__(kThreadsFwd, 1) query_tc_kernel(const TcParams
         // instructions themselves are predicated on one elected lane.  Warp 1 issues for heads 0 and 2, warp 14 for heads
         // 1 and 3 (consecutive steps alternate between the issuers); both walk the same global sequence of weight panels /
         // activation blocks and skip the other's entries.
-        const unsigned my_heads = __popc(q.head_mask) == 3 ? (warp == 1 ? q.head_mask : 0u) : (q.head_mask & (warp == 1 ? 5u : 10u));
+        const int me = warp == 1 ? 0 : 1;
+        const unsigned my_heads = q.head_mask & (me == 0 ? ~owner_mask : owner_mask);
+        uint32_t pw = 0, pa = 0;                    // parity of this issuer's next use of every weight / activation slot
         constexpr uint32_t idesc = make_idesc(kTileM, 128), idesc16 = make_idesc(kTileM, 16);
         const uint32_t ringA_lo = desc_lo(smem_u32(ringA)), ringAct_lo = desc_lo(smem_u32(ringAct)), ringW_lo = desc_lo(smem_u32(ringW));
         constexpr uint32_t kStageLo = kStageA >> 4, kPanelLo = kPanelBytes >> 4;
@@ -143,7 +149,8 @@ __global__ void __launch_bounds__(kThreadsFwd, 1) query_tc_kernel(const TcParams
                     }
                     const uint32_t d = tmem_base + h * 128;
                     const int s0 = u % kNW, s1 = (u + 1) % kNW;
-                    mbar_wait_t(&bars->w_full[s0], (u / kNW) & 1, DBG(3));       // panel w_hi: a_hi*w_hi + a_lo*w_hi
+                    mbar_wait_t(&bars->w_full[me][s0], (pw >> s0) & 1, DBG(3));   // panel w_hi: a_hi*w_hi + a_lo*w_hi
+                    pw ^= 1u << s0;
                     tc_fence_after();
                     const uint32_t w0 = ringW_lo + s0 * kPanelLo;
                     if (elect_one()) {
@@ -152,7 +159,8 @@ __global__ void __launch_bounds__(kThreadsFwd, 1) query_tc_kernel(const TcParams
                         umma_commit(&bars->w_empty[s0]);
                     }
                     __syncwarp();
-                    mbar_wait_t(&bars->w_full[s1], ((u + 1) / kNW) & 1, DBG(3));  // panel w_lo: a_hi*w_lo
+                    mbar_wait_t(&bars->w_full[me][s1], (pw >> s1) & 1, DBG(3));   // panel w_lo: a_hi*w_lo
+                    pw ^= 1u << s1;
                     tc_fence_after();
                     const uint32_t w1 = ringW_lo + s1 * kPanelLo;
                     if (elect_one()) {
@@ -176,8 +184,9 @@ __global__ void __launch_bounds__(kThreadsFwd, 1) query_tc_kernel(const TcParams
                     const uint32_t d = tmem_base + h * 128;
                     // both activation blocks must be complete before the accumulator is overwritten
                     const uint32_t b0 = actblk, b1 = actblk + 1;
-                    mbar_wait_t(&bars->act_full[b0 % kNACT], (b0 / kNACT) & 1, DBG(4));
-                    mbar_wait_t(&bars->act_full[b1 % kNACT], (b1 / kNACT) & 1, DBG(4));
+                    mbar_wait_t(&bars->act_full[me][b0 % kNACT], (pa >> (b0 % kNACT)) & 1, DBG(4));
+                    mbar_wait_t(&bars->act_full[me][b1 % kNACT], (pa >> (b1 % kNACT)) & 1, DBG(4));
+                    pa ^= (1u << (b0 % kNACT)) | (1u << (b1 % kNACT));
                     tc_fence_after();
                     if (layer < 3) {
 #pragma unroll 1
@@ -185,7 +194,8 @@ __global__ void __launch_bounds__(kThreadsFwd, 1) query_tc_kernel(const TcParams
                             const int sa = actblk % kNACT;
                             const uint32_t a_hi = ringAct_lo + sa * kStageLo, a_lo = a_hi + kPanelLo;
                             const int s0 = u % kNW, s1 = (u + 1) % kNW;
-                            mbar_wait_t(&bars->w_full[s0], (u / kNW) & 1, DBG(5));
+                            mbar_wait_t(&bars->w_full[me][s0], (pw >> s0) & 1, DBG(5));
+                            pw ^= 1u << s0;
                             tc_fence_after();
                             const uint32_t w0 = ringW_lo + s0 * kPanelLo;
                             if (elect_one()) {
@@ -193,7 +203,8 @@ __global__ void __launch_bounds__(kThreadsFwd, 1) query_tc_kernel(const TcParams
                                 umma_commit(&bars->w_empty[s0]);
                             }
                             __syncwarp();
-                            mbar_wait_t(&bars->w_full[s1], ((u + 1) / kNW) & 1, DBG(5));
+                            mbar_wait_t(&bars->w_full[me][s1], (pw >> s1) & 1, DBG(5));
+                            pw ^= 1u << s1;
                             tc_fence_after();
                             const uint32_t w1 = ringW_lo + s1 * kPanelLo;
                             if (elect_one()) {
@@ -208,7 +219,8 @@ __global__ void __launch_bounds__(kThreadsFwd, 1) query_tc_kernel(const TcParams
                     } else {
                         // last layer (<= 14 outputs, padded to N = 16): one 8 KB panel [kb0 hi | kb0 lo | kb1 hi | kb1 lo]
                         const int s0 = u % kNW;
-                        mbar_wait_t(&bars->w_full[s0], (u / kNW) & 1, DBG(5));
+                        mbar_wait_t(&bars->w_full[me][s0], (pw >> s0) & 1, DBG(5));
+                        pw ^= 1u << s0;
                         tc_fence_after();
                         const uint32_t w = ringW_lo + s0 * kPanelLo;
                         const int sa0 = actblk % kNACT, sa1 = (actblk + 1) % kNACT;
@@ -332,7 +344,7 @@ __global__ void __launch_bounds__(kThreadsFwd, 1) query_tc_kernel(const TcParams
                         tc_fence_before();
                         fence_proxy_async();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&bars->act_full[sa]);
+                        if (lane == 0) mbar_arrive(&bars->act_full[(owner_mask >> h) & 1][sa]);
                         actblk += 2;
                     } else {
                         // last layer: 16 accumulator columns -> + bias -> OUT_DIST mask -> HBM (reference layout)
