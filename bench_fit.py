@@ -73,7 +73,7 @@ def bench_gen(net, dev, img_host, args):
     count fixes the number of outer iterations at 4 per field = 80 forward + 80 backward queries of 20-30 k points."""
     import chore_b200
     B = img_host.shape[0]
-    gen = chore_b200.Generator(net, filter_val=1e9, device=str(dev))
+    gen = chore_b200.Generator(net, filter_val=1e9, device=str(dev), rng=args.rng)
     cc = torch.tensor([[1008., 995.]], device=dev).repeat(B, 1)
     net.filter(img_host.to(dev))
 
@@ -101,6 +101,8 @@ def bench_gen(net, dev, img_host, args):
                       "points_returned_per_field": n, "outer_iterations_per_field": 4, "projection_steps": 10,
                       "queries": "80 x (df forward + gradient to the points) of 20-30k points + 8 x all-head forward",
                       "higher_is_better": False, "data": "synthetic", "dtype": "f32",
+                      "rng": args.rng + (" (resampling on the device, no host round trip inside an outer iteration)" if args.rng == "device"
+                                         else " (torch CPU draws in the reference's order: bit-identical sample sets)"),
                       "note": "reference on CPU: 1.44 s per forward+backward at 20 k points (SURVEY.md section 6) => ~2 min for the same loop"}),
           flush=True)
 
@@ -112,6 +114,7 @@ def main():
     ap.add_argument("--points", type=int, default=20000)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--no-graph", action="store_true", help="launch the fused steps directly (for ncu launch lists)")
+    ap.add_argument("--rng", default="device", choices=["device", "reference"], help="--gen: where the resampling draws come from")
     ap.add_argument("--gen", action="store_true", help="time Generator.gen_pc_batch (neural point cloud stage) instead of the fit loop")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -140,15 +143,19 @@ def main():
 
     def build():
         split, (R, t, s), fused = build_state()
-        return split, (R, t, s), ((fused.smpl_step, fused.object_step) if args.no_graph else fused.graphed())
+        # product path: SMPL step + object step forked onto two streams inside ONE CUDA graph per iteration
+        return split, (R, t, s), ((fused.smpl_step, fused.object_step) if args.no_graph else (fused.graphed_iteration(), None)), fused
 
     def job(state):
-        split, (R, t, s), (g_smpl, g_obj) = state
+        split, (R, t, s), (g_smpl, g_obj), fused = state
         net.filter(img_host.to(dev, non_blocking=True))
         net.query(pts, crop_center=cc)
-        for _ in range(args.iters):
+        for it in range(args.iters):
+            if it % 10 == 0:
+                fused.zero_grad()                    # the reference loops: optimizer.zero_grad() once per 10 inner steps
             g_smpl()
-            g_obj()
+            if g_obj is not None:
+                g_obj()
         fitted = torch.cat([split.global_pose, split.body_pose, split.hand_pose, split.top_betas, split.other_betas, split.trans,
                             R.reshape(B, 9), t, s.reshape(B, 1)], 1).detach()
         return cdist.gather_results(fitted.t().contiguous(), dim=1).t()      # (batch, 182) on every rank
