@@ -307,8 +307,12 @@ __global__ void __launch_bounds__(kThreadsFwd, 1) query_tc_kernel(const TcParams
 #pragma unroll 1
                 for (int h = 0; h < 4; ++h) {
                     if (!((q.head_mask >> h) & 1)) continue;             // head not requested: nothing was computed
+                    // every warp observes EVERY completion of tm_full[h] (4 per tile: parity = layer & 1), also the group that has
+                    // no output-layer work for this head: a warp that skipped the wait would test the next tile's layer-1 phase
+                    // one phase early, pass on the parity of layer 3 and read a stale accumulator (seen with single-head masks
+                    // on more than 148 tiles, where one group has no output-layer work at all)
+                    mbar_wait_t(&bars->tm_full[h], layer & 1, DBG(7));
                     if (layer == 3 && (h & 1) != colhalf) continue;      // last layer: the heads are split between the groups
-                    mbar_wait_t(&bars->tm_full[h], layer & 1, DBG(7));   // 4 completions per tile: parity = layer & 1
                     tc_fence_after();
                     if (layer < 3) {
                         // bias + ReLU + hi/lo split -> activation k-block `colhalf` of head h

@@ -328,7 +328,10 @@ __global__ void __launch_bounds__(kThreads, 1) query_tc2_kernel(const TcParams q
             for (int layer = 0; layer < 4; ++layer) {
 #pragma unroll 1
                 for (int h = 0; h < 4; ++h) {
-                    if (layer == 3 && (h & 1) != colhalf) continue;      // last layer: the heads are split between the groups
+                    if (layer == 3 && (h & 1) != colhalf) {              // last layer: the heads are split between the groups
+                        mbar_wait_t(&bars->tm_full[h], layer & 1, nullptr);      // ... but every warp observes every phase (query_tc.cu)
+                        continue;
+                    }
                     if (layer < 3) {
                         // bias + ReLU + hi/lo split -> activation k-block `colhalf` of head h
                         mbar_wait_t(&bars->tm_full[h], layer & 1, DBG(0));         // 4 completions per tile: parity = layer & 1

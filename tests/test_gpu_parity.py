@@ -1025,6 +1025,29 @@ def test_query_bwd_concurrent_heads_equal_sequential(net):
         assert torch.equal(seq, con), (k, (seq - con).abs().max().item())
 
 
+def test_partial_head_masks_on_many_tiles_are_bit_identical(net):
+    """Regression: with more tiles than SMs (a CTA walks several tiles) and a mask that leaves one epilogue group without
+    output-layer work (single heads, {0,2}, {1,3}) that group used to skip a completion of the accumulator barrier, test the
+    next tile's layer-1 phase one phase early and read a stale accumulator (nondeterministic rows in the second tile of
+    a CTA).  HEAD_DF alone is what Generator.approx_surface and the fitter use on 20-30 k points = 157-235 tiles."""
+    feat, tmpx = O.synth_features(5, B=2)
+    set_maps(net, feat, tmpx)
+    f, s = net._maps()
+    cc = torch.tensor([[1008., 995.], [990., 1001.]], device=DEV)
+    pts = torch.cat([O.synth_points("frustum", 7, 2, 5000), O.synth_points("init_box", 8, 2, 30001)], 1).to(DEV)
+    full, _ = net.handle.query_fwd(f, s, pts, cc, 15)
+    full = [x.clone() for x in full]
+    for mask in (1, 2, 4, 8, 5, 10, 3, 12, 7, 14):
+        for rep in range(2):
+            got, _ = net.handle.query_fwd(f, s, pts, cc, mask)
+            torch.cuda.synchronize()
+            for h in range(4):
+                if (mask >> h) & 1:
+                    assert torch.equal(got[h], full[h]), (mask, h, rep, (got[h] - full[h]).abs().max().item())
+                else:
+                    assert got[h] is None
+
+
 def test_projected_map_grid_query_matches_per_point_kernel(net, sd, monkeypatch):
     """query_g.cu (opt-in, CHORE_B200_QUERY_PRE=1): layer 1 applied once per pixel (W1 . feat, W1 . skip as 1x1 convolutions on the
     encoder's tensor-core kernel), then bilinear taps of the projected maps.  Same function as model/chore.py:107-167 up to
