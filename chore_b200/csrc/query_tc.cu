@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(kThreads, 1) query_bwd_tc_kernel(const TcParam
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&bars->a_full[i], 4); mbar_init(&bars->a_empty[i], 1);
+            mbar_init(&bars->a_full[i], 12); mbar_init(&bars->a_empty[i], 1);      // 4 gather + 8 (otherwise idle) epilogue warps
             mbar_init(&bars->act_full[i], 4); mbar_init(&bars->act_empty[i], 1);
         }
         for (int i = 0; i < kBwdNW; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
@@ -544,7 +544,9 @@ __global__ void __launch_bounds__(kThreads, 1) query_bwd_tc_kernel(const TcParam
             ++pass;
         }
     } else if (warp < kEpiWarp0) {
-        // ---------------- gather warps (same as the forward kernel, one pass per work item) ----------------
+        // ---------------- gather warps: rows [0, 64) of every feature k-block, 16 rows each (the epilogue warps, idle until
+        // layer 1 is complete, gather rows [64, 128): the recompute of layer 1 for ONE head needs the whole 6-block operand, so
+        // the gather is what bounds a work item) ----------------
         const int g = warp - kGatherWarp0;
         const int half = lane >> 4, l16 = lane & 15;
         uint32_t ablk = 0;
@@ -556,7 +558,7 @@ __global__ void __launch_bounds__(kThreads, 1) query_bwd_tc_kernel(const TcParam
             const float *F = q.feat + (size_t)b * q.fh * q.fw * kFeatC;
             const float *S = q.skip + (size_t)b * (2 * q.fh) * (2 * q.fw) * kSkipC;
             float my_x = 0.f, my_y = 0.f, my_z = 1.f, my_nx, my_ny;
-            if (n0 + g * 32 + lane < q.n_count) load_point(q, b, n0 + g * 32 + lane, my_x, my_y, my_z);
+            if (n0 + g * 16 + l16 < q.n_count) load_point(q, b, n0 + g * 16 + l16, my_x, my_y, my_z);      // lanes L and L + 16: row 16 g + L
             project_tc(my_x, my_y, my_z, ccx, ccy, my_nx, my_ny);
             const LaneTaps tapsF = make_lane_taps(my_nx, my_ny, q.fh, q.fw, kFeatC), tapsS = make_lane_taps(my_nx, my_ny, 2 * q.fh, 2 * q.fw, kSkipC);
             for (int kb = 0; kb < kL1Blocks; ++kb, ++ablk) {
@@ -565,10 +567,10 @@ __global__ void __launch_bounds__(kThreads, 1) query_bwd_tc_kernel(const TcParam
                 uint8_t *hi = ringA + (size_t)sa * kStageA, *lo = hi + kPanelBytes;
                 if (kb < 5) {
                     const bool is_feat = kb < 4;
-                    gather_kblock_p<32, kGatherBatch>((is_feat ? F + kb * 64 : S) + l16 * 4, (is_feat ? q.fw * kFeatC : 2 * q.fw * kSkipC),
+                    gather_kblock_p<16, kGatherBatch>((is_feat ? F + kb * 64 : S) + l16 * 4, (is_feat ? q.fw * kFeatC : 2 * q.fw * kSkipC),
                                                       is_feat ? kFeatC : kSkipC, is_feat ? tapsF : tapsS, g, half, l16, hi, lo);
-                } else {
-                    const int r = g * 32 + lane;
+                } else if (lane < 16) {
+                    const int r = g * 16 + lane;
                     uint32_t h01, l01, h23, l23;
                     split2(my_x, my_y, h01, l01);
                     split2(__fsub_rn(my_z, 2.2f), 0.f, h23, l23);
@@ -589,7 +591,7 @@ __global__ void __launch_bounds__(kThreads, 1) query_bwd_tc_kernel(const TcParam
         const int row = quarter * 32 + lane;
         uint8_t *hi = ringAct + (size_t)colhalf * kStageA, *lo = hi + kPanelBytes;     // this warp's activation block
         const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + colhalf * 64;
-        uint32_t pass = 0;
+        uint32_t pass = 0, ablk = 0;
         for (long long item = first_tile; item < total_items; item += tile_stride) {
             const long long tile = item / nslots;
             const int slot = (int)(item % nslots);
@@ -609,6 +611,40 @@ __global__ void __launch_bounds__(kThreads, 1) query_bwd_tc_kernel(const TcParam
                 const bool use = live && !(hd == 0 && !inimg);
 #pragma unroll
                 for (int o = 0; o < 14; ++o) gout[o] = (use && o < nout) ? __ldg(g_head + ((size_t)b * nout + o) * q.N + q.n_start + n) : 0.f;
+            }
+            {
+                // ---- rows [64 + 8 e, 64 + 8 e + 8) of the six layer-1 operand blocks ----
+                const long long n0 = (tile % q.tiles_per_b) * kTileM;
+                const int half = lane >> 4, l16 = lane & 15, l8 = lane & 7;
+                const float ccx = __ldg(q.crop_center + b * 2), ccy = __ldg(q.crop_center + b * 2 + 1);
+                const float *F = q.feat + (size_t)b * q.fh * q.fw * kFeatC;
+                const float *S = q.skip + (size_t)b * (2 * q.fh) * (2 * q.fw) * kSkipC;
+                float hx = 0.f, hy = 0.f, hz = 1.f, hnx, hny;
+                if (n0 + 64 + e * 8 + l8 < q.n_count) load_point(q, b, n0 + 64 + e * 8 + l8, hx, hy, hz);      // lane L: row 64 + 8 e + (L & 7)
+                project_tc(hx, hy, hz, ccx, ccy, hnx, hny);
+                const LaneTaps tapsF = make_lane_taps(hnx, hny, q.fh, q.fw, kFeatC), tapsS = make_lane_taps(hnx, hny, 2 * q.fh, 2 * q.fw, kSkipC);
+                for (int kb = 0; kb < kL1Blocks; ++kb, ++ablk) {
+                    const int sa = ablk % 2;
+                    mbar_wait(&bars->a_empty[sa], ((ablk / 2) & 1) ^ 1);
+                    uint8_t *ahi = ringA + (size_t)sa * kStageA, *alo = ahi + kPanelBytes;
+                    if (kb < 5) {
+                        const bool is_feat = kb < 4;
+                        gather_kblock_p<8, kGatherBatch>((is_feat ? F + kb * 64 : S) + l16 * 4, (is_feat ? q.fw * kFeatC : 2 * q.fw * kSkipC),
+                                                         is_feat ? kFeatC : kSkipC, is_feat ? tapsF : tapsS, 8 + e, half, l16, ahi, alo);
+                    } else if (lane < 8) {
+                        const int r = 64 + e * 8 + lane;
+                        uint32_t h01, l01, h23, l23;
+                        split2(hx, hy, h01, l01);
+                        split2(__fsub_rn(hz, 2.2f), 0.f, h23, l23);
+                        *reinterpret_cast<uint4 *>(ahi + sw128(r, 0)) = make_uint4(h01, h23, 0u, 0u);
+                        *reinterpret_cast<uint4 *>(alo + sw128(r, 0)) = make_uint4(l01, l23, 0u, 0u);
+                        *reinterpret_cast<uint4 *>(ahi + sw128(r, 1)) = make_uint4(0u, 0u, 0u, 0u);
+                        *reinterpret_cast<uint4 *>(alo + sw128(r, 1)) = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars->a_full[sa]);
+                }
             }
             uint32_t mask[3][2];
             // ---- forward recompute: F1, F2, F3 ----
