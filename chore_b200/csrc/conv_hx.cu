@@ -539,7 +539,12 @@ __global__ void __launch_bounds__(kThreadsHx, 1) conv_hx_kernel(const HxParams p
                     double *gst = set ? a.st_out : a.st_raw;
                     double val = 0.0;
 #pragma unroll
-                    for (int w = 0; w < 12; ++w) { val += (double)ctl->stp[w][set][idx]; ctl->stp[w][set][idx] = 0.f; }
+                    for (int w = 0; w < 12; ++w) {
+                        // a non-last item is finished by worker 0 of every lane quarter alone; the helper slots may already hold
+                        // partial sums of the CTA's LAST item (another image when B > 1), which the helpers started meanwhile
+                        if (!last && (w % 3) != 0) continue;
+                        val += (double)ctl->stp[w][set][idx]; ctl->stp[w][set][idx] = 0.f;
+                    }
                     if (gst != nullptr && val != 0.0) atomicAdd(gst + (size_t)b * kGroups * 2 + idx, val);
                 }
                 if (!last) named_bar(1, 128);            // the slots are clear before the next item writes them
@@ -664,7 +669,11 @@ int conv_hx_launch(chore_handle *h, const ConvHxArgs &a, const ConvHxPlan &pl, f
     p.n_slots = slots > kMaxSlots ? kMaxSlots : slots;
     CHORE_CHECK(p.n_slots >= 2, "conv_hx: weight ring does not fit (Ns %d)", p.Ns);
     const size_t smem = fixed + (size_t)p.n_slots * p.w_slot;
-    const int grid = p.n_items < h->sm_count ? p.n_items : h->sm_count;
+    int grid = p.n_items < h->sm_count ? p.n_items : h->sm_count;
+    if (const char *e = getenv("CHORE_B200_HX_GRID")) {      // debugging aid: "items" = one work item per CTA (several waves)
+        if (strcmp(e, "items") == 0) grid = p.n_items;
+        else if (atoi(e) > 0 && atoi(e) < grid) grid = atoi(e);
+    }
     p.trace = (g_hx_trace != nullptr && g_hx_trace_idx < 256) ? g_hx_trace + 32 * (g_hx_trace_idx++) : nullptr;
     if (pl.k_splits > 1) {
         // one cluster per (tile, n slice): rank = K part; the received partials live in the halo buffers + weight ring

@@ -699,6 +699,13 @@ int encoder_load_weights(chore_handle *h, const std::map<std::string, const chor
             CHORE_CUDA(cudaMemcpy(dev, dst.data(), n * sizeof(float), cudaMemcpyHostToDevice));
             ConvW &w = e.conv[base];
             w.w = dev; w.kh = kh; w.kw = kw; w.cin = ci; w.cout = co;
+            if (base == "image_filter.conv1" && encoder_mode() == "hx" && ci * kh * kw <= 256 && co % 32 == 0) {
+                // stem as a 1x1 convolution over im2col columns (encoder_hx.cu): [co][k = (ci, ky, kx)], zero padded to 256
+                std::vector<float> wst((size_t)co * 256, 0.f);
+                for (int o = 0; o < co; ++o)
+                    for (int k = 0; k < ci * kh * kw; ++k) wst[(size_t)o * 256 + k] = src[(size_t)o * ci * kh * kw + k];
+                if (int rc = conv_hx_pack_weights(h, wst.data(), co, 256, 1, 1, &w.whx)) return rc;
+            }
             if (base != "image_filter.conv1" && (kh == 1 || kh == 3) && co % 32 == 0 && co <= 256) {
                 const std::string mode = encoder_mode();
                 if (mode == "hx") {

@@ -421,11 +421,57 @@ ActH hourglass(CtxH &c, const std::string &p, int level, const ActH &x) {
 
 constexpr int kNumStack = 5, kDepth = 2;
 
+// im2col of the 7x7 stride-2 pad-3 stem (model/HGFilters.py:149): NCHW image -> (B, H/2 * W/2, 256) columns, k = (c, ky, kx)
+// (245 values, zero padded), so that the stem runs as a 1x1 convolution on the tensor cores (conv_hx_kernel<1>, K = 256)
+// with bias and GroupNorm statistics in its epilogue.  One float4 of columns per thread; the image stays in L1 / L2.
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float *__restrict__ img, int H, int W, float *__restrict__ col, size_t total4) {
+    chore_pdl_launch_dependents();
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= total4) return;
+    const int OH = H / 2, OW = W / 2;
+    const int q = (int)(i & 63);
+    const size_t px = i >> 6;
+    const int ox = (int)(px % OW);
+    const size_t t = px / OW;
+    const int oy = (int)(t % OH), b = (int)(t / OH);
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int k = q * 4 + j;
+        const int c = k / 49, r = k - c * 49, ky = r / 7, kx = r - ky * 7;
+        const int iy = 2 * oy + ky - 3, ix = 2 * ox + kx - 3;
+        const bool ok = k < CHORE_IN_CH * 49 && iy >= 0 && iy < H && ix >= 0 && ix < W;
+        v[j] = ok ? __ldg(img + (((size_t)b * CHORE_IN_CH + c) * H + iy) * W + ix) : 0.f;
+    }
+    reinterpret_cast<float4 *>(col)[i] = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+static bool stem_on_tensor_cores() {
+    static const bool on = [] {
+        const char *e = getenv("CHORE_B200_STEM");
+        return !(e != nullptr && strcmp(e, "simt") == 0);
+    }();
+    return on;
+}
+
 void run_graph(CtxH &c, const float *images, int H, int W, float *feat, float *skip, float *normx) {
     const std::string p = "image_filter";
     const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4;
     ActH s0 = c.act(64, H2, W2, true);
-    {
+    if (stem_on_tensor_cores() && cw(c, p + ".conv1").whx != nullptr) {
+        const size_t mark = c.top;
+        ActH col = c.act(256, H2, W2, false);            // 67 MB per 512^2 image, released right after the convolution
+        const size_t total4 = (size_t)c.B * H2 * W2 * 64;
+        HX_LAUNCH(c, stem_im2col_kernel, (unsigned)((total4 + 255) / 256), 256, 0, images, H, W, col.p, total4);
+        ConvW w = cw(c, p + ".conv1");
+        w.kh = w.kw = 1; w.cin = 256;
+        ConvSpec s;
+        s.in = &col;
+        s.out = s0.p; s.ld_out = 64;
+        s.st_out = s0.st; s.c_out_total = 64;
+        conv(c, w, s);
+        c.top = mark;
+    } else {
         dim3 grid((W2 + kStemTile - 1) / kStemTile, (H2 + kStemTile - 1) / kStemTile, c.B);
         const size_t smem = (size_t)(kStemPatchFloats + CHORE_IN_CH * 49 * 64) * sizeof(float);
         const ConvW &w = cw(c, p + ".conv1");

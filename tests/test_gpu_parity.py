@@ -235,6 +235,20 @@ def test_encoder_vs_golden_512(net):
     assert abs(ck[0] - g["feat_ck"][0]) < 1e-3 * abs(g["feat_ck"][2]) * feat.numel() ** 0.5
 
 
+def test_encoder_batched_equals_per_image(net):
+    """B > 1 at the production size: a CTA of the conv kernels then walks work items of DIFFERENT images (128 tiles per image
+    at 128^2 on 148 SMs), so per-image GroupNorm statistics, table switches and the helpers' statistics slots are all
+    exercised; the result must be the per-image result (regression: helper slots of the next image's item were flushed into
+    the previous image's sums)."""
+    img = O.synth_images(3, B=3, size=512).to(DEV)
+    fb, sb, nb = [o.clone() for o in net.handle.encode(img)]
+    for i in range(3):
+        f1, s1, n1 = net.handle.encode(img[i:i + 1].clone())
+        torch.cuda.synchronize()
+        for name, a, b in (("feat", fb[i:i + 1], f1), ("skip", sb[i:i + 1], s1), ("normx", nb[i:i + 1], n1)):
+            assert rel_err(a, b) < 5e-5, (i, name, rel_err(a, b))      # summation order of the fp64 statistics atomics only
+
+
 def test_encoder_refinit_weights():
     import chore_b200
     g = load_golden("encoder_128_refinit.npz")
