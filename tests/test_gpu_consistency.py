@@ -120,3 +120,39 @@ def test_lbs_batched_equals_per_item():
         one = run(slice(i, i + 1))
         for name, a, b in zip(("verts", "jtr", "g_pose", "g_betas", "g_trans", "g_offsets"), full, one):
             assert rel_err(a[i:i + 1], b) < 1e-5, (i, name, rel_err(a[i:i + 1], b))
+
+
+_ENC_SHAPES = [(3, 512, 512), (2, 384, 512), (5, 256, 256), (2, 128, 192), (1, 64, 64), (9, 128, 128)]
+_ENC_CHILD = r"""
+import sys, torch
+sys.path.insert(0, sys.argv[1])
+import chore_b200
+from oracle import chore_oracle as O
+net = chore_b200.CHORE(device="cuda:0")
+net.load_state_dict(O.make_state_dict(0, "unit"))
+out = {}
+for (B, H, W) in eval(sys.argv[3]):
+    g = torch.Generator().manual_seed(B * 1000 + H + W)
+    img = torch.rand(B, 5, H, W, generator=g)
+    img[:, 3:] = (img[:, 3:] > 0.5).float()
+    out[(B, H, W)] = [t.cpu() for t in net.handle.encode(img.to("cuda:0"))]
+torch.cuda.synchronize()
+torch.save(out, sys.argv[2])
+"""
+
+
+def test_encoder_matches_round1_encoder_across_shapes(tmp_path):
+    """Two independent implementations of the hourglass encoder -- conv_hx.cu / encoder_hx.cu (halo tiles, GroupNorm folded into
+    the convolutions, cluster K split) and the round-1 conv_tc.cu / encoder.cu (TMA im2col, separate statistics kernels) -- on
+    batched, non-square and small inputs.  The implementation is chosen per process (CHORE_B200_ENCODER), hence the children."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for mode in ("tc1", "hx"):
+        path = str(tmp_path / f"enc_{mode}.pt")
+        env = dict(os.environ, CHORE_B200_ENCODER=mode)
+        subprocess.run([sys.executable, "-c", _ENC_CHILD, root, path, repr(_ENC_SHAPES)], check=True, env=env, timeout=300)
+        outs[mode] = torch.load(path)
+    for k in _ENC_SHAPES:
+        for name, a, b in zip(("feat", "skip", "normx"), outs["hx"][k], outs["tc1"][k]):
+            assert rel_err(a, b) < 5e-5, (k, name, rel_err(a, b))
