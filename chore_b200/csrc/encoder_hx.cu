@@ -265,6 +265,11 @@ struct CtxH {
     char *zbase = nullptr;       // arena that is zeroed at the start of every encode: statistics slots, K-split counters
     size_t ztop = 0;
     int rc = 0;
+    // fork / join of the hourglass branches (see hourglass()): side streams and events, owned by the EncoderPlan
+    cudaStream_t side[2] = {nullptr, nullptr};
+    cudaEvent_t *events = nullptr;
+    int n_events = 0, ev_next = 0;
+    int hold = 0;                // > 0: temporaries stay allocated (their kernels run concurrently with what is recorded next)
 
     float *alloc(size_t floats) {
         const size_t bytes = (floats * sizeof(float) + 255) / 256 * 256;
@@ -391,7 +396,7 @@ ActH conv_block(CtxH &c, const std::string &p, const ActH &x, int cout, bool wan
         s.st_out = out.st; s.c_out_total = cout;
         conv(c, cw(c, p + ".conv3"), s);
     }
-    c.top = mark;   // t1, t2 are dead (stream order makes reuse safe)
+    if (c.hold == 0) c.top = mark;   // t1, t2 are dead (stream order makes reuse safe; a forked branch keeps them until the join)
     return out;
 }
 
@@ -405,14 +410,50 @@ ActH avgpool(CtxH &c, const ActH &x, bool want_stats, float *dst = nullptr) {
 }
 
 // HourGlass._forward (model/HGFilters.py:26-50); the result carries statistics (its consumer normalises it)
+// The skip branch (up1 = ConvBlock at this resolution) and the low-resolution path (pool, ConvBlocks / inner hourglass) are
+// independent until the upsample + add.  The low-resolution convolutions occupy 48 - 96 SMs for a few microseconds each, so the
+// skip branch is recorded on a side stream (an edge-free pair of chains in the captured graph) and joined before the add:
+// its four launches then run beside the low path instead of in front of it.
+static int fork_levels() {
+    static const int n = [] {
+        const char *e = getenv("CHORE_B200_HX_FORK");
+        return e != nullptr ? atoi(e) : 2;
+    }();
+    return n;
+}
+
 ActH hourglass(CtxH &c, const std::string &p, int level, const ActH &x) {
     const std::string L = std::to_string(level);
-    ActH up1 = conv_block(c, p + ".b1_" + L, x, x.C, false);
-    const size_t mark = c.top;
+    const bool fork = level <= fork_levels() && level <= 2 && (c.dry || (c.side[level - 1] != nullptr && c.ev_next + 2 <= c.n_events));
+    ActH up1;
+    size_t mark;
+    cudaEvent_t ev_join = nullptr;
+    if (fork) {
+        up1 = c.act(x.C, x.H, x.W, false);
+        mark = c.top;                                    // everything above up1 is released at the end, the side branch's temporaries too
+        cudaStream_t main_st = c.st;
+        if (!c.dry && c.rc == 0) {
+            cudaEvent_t ev_fork = c.events[c.ev_next++];
+            ev_join = c.events[c.ev_next++];
+            if (cudaEventRecord(ev_fork, main_st) != cudaSuccess || cudaStreamWaitEvent(c.side[level - 1], ev_fork, 0) != cudaSuccess) c.rc = CHORE_ERR_CUDA;
+            c.st = c.side[level - 1];
+        }
+        ++c.hold;
+        conv_block(c, p + ".b1_" + L, x, x.C, false, up1);
+        --c.hold;
+        if (!c.dry) {
+            if (c.rc == 0 && cudaEventRecord(ev_join, c.st) != cudaSuccess) c.rc = CHORE_ERR_CUDA;
+            c.st = main_st;
+        }
+    } else {
+        up1 = conv_block(c, p + ".b1_" + L, x, x.C, false);
+        mark = c.top;
+    }
     ActH low1 = conv_block(c, p + ".b2_" + L, avgpool(c, x, true), x.C, true);
     ActH low2 = level > 1 ? hourglass(c, p, level - 1, low1) : conv_block(c, p + ".b2_plus_" + L, low1, x.C, true);
     ActH low3 = conv_block(c, p + ".b3_" + L, low2, x.C, false);
     up1.st = c.slot();
+    if (fork && !c.dry && c.rc == 0 && cudaStreamWaitEvent(c.st, ev_join, 0) != cudaSuccess) c.rc = CHORE_ERR_CUDA;
     const size_t n4 = (size_t)up1.H * up1.W * up1.C / 4;
     HX_LAUNCH(c, upadd_stats_kernel, dim3(ew_grid(c, n4), c.B), 256, 0, low3.p, up1.p, low3.H, low3.W, low3.C, up1.st);
     c.top = mark;
@@ -544,6 +585,8 @@ struct EncoderPlan {
     };
     std::vector<Entry> entries;
     cudaStream_t cap_stream = nullptr;
+    cudaStream_t side[2] = {nullptr, nullptr};      // hourglass skip branches (fork / join)
+    std::vector<cudaEvent_t> events;
     bool stem_configured = false;
 };
 
@@ -551,6 +594,8 @@ void encoder_plan_destroy(chore_handle *h) {
     if (!h->enc_plan) return;
     for (auto &e : h->enc_plan->entries) cudaGraphExecDestroy(e.exec);
     if (h->enc_plan->cap_stream) cudaStreamDestroy(h->enc_plan->cap_stream);
+    for (cudaStream_t s : h->enc_plan->side) if (s) cudaStreamDestroy(s);
+    for (cudaEvent_t e : h->enc_plan->events) cudaEventDestroy(e);
     delete h->enc_plan;
     h->enc_plan = nullptr;
 }
@@ -588,11 +633,18 @@ int encode_hx(chore_handle *h, const float *images, int B, int H, int W, float *
         CHORE_CUDA(cudaFuncSetAttribute(stem_hx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         plan.stem_configured = true;
     }
+    if (plan.events.empty()) {
+        for (cudaStream_t &s : plan.side) CHORE_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        plan.events.resize(2 * kNumStack * kDepth);
+        for (cudaEvent_t &e : plan.events) CHORE_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     auto record = [&](cudaStream_t s) -> int {
         CtxH c{};
         c.h = h; c.B = B; c.dry = false; c.st = s;
         c.base = static_cast<char *>(h->ws);
         c.zbase = static_cast<char *>(h->ws2);
+        c.side[0] = plan.side[0]; c.side[1] = plan.side[1];
+        c.events = plan.events.data(); c.n_events = (int)plan.events.size();
         CHORE_CUDA(cudaMemsetAsync(h->ws2, 0, gn_bytes, s));
         run_graph(c, images, H, W, feat, skip, normx);
         return c.rc;
