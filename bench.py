@@ -465,8 +465,12 @@ def run_ours(args, rank, world, local_rank):
         df, pca, parts, centers = net.get_preds()
         out20_host.copy_(torch.cat([df[0], pca.reshape(1, 9, -1)[0], parts[0], centers[0]], 0), non_blocking=True)
 
+    # chore_encode caches one CUDA graph per set of buffer addresses; the e2e call allocates its tensors afresh, so the
+    # caching allocator needs a few rounds before the handful of address combinations it cycles through are all captured
     for _ in range(3):
-        image20k_device(); image20k_e2e()
+        image20k_device()
+    for _ in range(max(10, args.warmup)):
+        image20k_e2e()
     barrier()
     reps20 = max(10, args.steps)
     ms20 = max_over_ranks(sum(timed(image20k_device, reps20))) / reps20

@@ -584,6 +584,12 @@ struct EncoderPlan {
         uint64_t kernels;
     };
     std::vector<Entry> entries;
+    // callers whose buffers come from a cycling allocator would make every call a new address combination (= a new capture of
+    // ~2 ms); after kMaxSpecific address-specific graphs per shape the encode runs a generic graph on handle-owned staging
+    // buffers and copies the image in and the maps out (42 MB of device-to-device copies per 512 x 512 image, ~1 % of the encode)
+    static constexpr int kMaxSpecific = 4;
+    float *gen_buf = nullptr;
+    size_t gen_floats = 0;
     cudaStream_t cap_stream = nullptr;
     cudaStream_t side[2] = {nullptr, nullptr};      // hourglass skip branches (fork / join)
     std::vector<cudaEvent_t> events;
@@ -594,6 +600,7 @@ void encoder_plan_destroy(chore_handle *h) {
     if (!h->enc_plan) return;
     for (auto &e : h->enc_plan->entries) cudaGraphExecDestroy(e.exec);
     if (h->enc_plan->cap_stream) cudaStreamDestroy(h->enc_plan->cap_stream);
+    if (h->enc_plan->gen_buf) cudaFree(h->enc_plan->gen_buf);
     for (cudaStream_t s : h->enc_plan->side) if (s) cudaStreamDestroy(s);
     for (cudaEvent_t e : h->enc_plan->events) cudaEventDestroy(e);
     delete h->enc_plan;
@@ -638,7 +645,7 @@ int encode_hx(chore_handle *h, const float *images, int B, int H, int W, float *
         plan.events.resize(2 * kNumStack * kDepth);
         for (cudaEvent_t &e : plan.events) CHORE_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
-    auto record = [&](cudaStream_t s) -> int {
+    auto record = [&](cudaStream_t s, const float *im, float *ft, float *sk, float *nx) -> int {
         CtxH c{};
         c.h = h; c.B = B; c.dry = false; c.st = s;
         c.base = static_cast<char *>(h->ws);
@@ -646,43 +653,80 @@ int encode_hx(chore_handle *h, const float *images, int B, int H, int W, float *
         c.side[0] = plan.side[0]; c.side[1] = plan.side[1];
         c.events = plan.events.data(); c.n_events = (int)plan.events.size();
         CHORE_CUDA(cudaMemsetAsync(h->ws2, 0, gn_bytes, s));
-        run_graph(c, images, H, W, feat, skip, normx);
+        run_graph(c, im, H, W, ft, sk, nx);
         return c.rc;
     };
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (st != nullptr && cudaStreamIsCapturing(st, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
-    if (!graphs_enabled() || cap != cudaStreamCaptureStatusNone) return record(st);
+    if (!graphs_enabled() || cap != cudaStreamCaptureStatusNone) return record(st, images, feat, skip, normx);
 
-    for (auto &e : plan.entries)
-        if (e.images == images && e.feat == feat && e.skip == skip && e.normx == normx && e.ws == h->ws && e.ws2 == h->ws2 &&
-            e.B == B && e.H == H && e.W == W) {
-            CHORE_CUDA(cudaGraphLaunch(e.exec, st));
-            g_launch_count.fetch_add(e.kernels, std::memory_order_relaxed);
+    auto find = [&](const void *im, void *ft, void *sk, void *nx) -> EncoderPlan::Entry * {
+        for (auto &e : plan.entries)
+            if (e.images == im && e.feat == ft && e.skip == sk && e.normx == nx && e.ws == h->ws && e.ws2 == h->ws2 && e.B == B && e.H == H && e.W == W)
+                return &e;
+        return nullptr;
+    };
+    auto capture = [&](const float *im, float *ft, float *sk, float *nx, EncoderPlan::Entry **out) -> int {
+        if (!plan.cap_stream) CHORE_CUDA(cudaStreamCreateWithFlags(&plan.cap_stream, cudaStreamNonBlocking));
+        const uint64_t before = g_launch_count.load();
+        CHORE_CUDA(cudaStreamBeginCapture(plan.cap_stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = record(plan.cap_stream, im, ft, sk, nx);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(plan.cap_stream, &graph);
+        const uint64_t kernels = g_launch_count.load() - before;
+        g_launch_count.fetch_sub(kernels, std::memory_order_relaxed);   // recorded, not executed
+        if (rc != CHORE_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) {
+            chore_set_error("encoder graph capture failed: %s", cudaGetErrorString(ce));
+            return CHORE_ERR_CUDA;
+        }
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) {
+            chore_set_error("encoder graph instantiation failed: %s", cudaGetErrorString(ie));
+            return CHORE_ERR_CUDA;
+        }
+        if (plan.entries.size() >= 16) { cudaGraphExecDestroy(plan.entries.front().exec); plan.entries.erase(plan.entries.begin()); }
+        plan.entries.push_back({im, ft, sk, nx, h->ws, h->ws2, B, H, W, exec, kernels});
+        *out = &plan.entries.back();
+        return CHORE_OK;
+    };
+    EncoderPlan::Entry *e = find(images, feat, skip, normx);
+    if (e == nullptr) {
+        int specific = 0;
+        for (auto &x : plan.entries)
+            if (x.B == B && x.H == H && x.W == W && x.ws == h->ws && x.ws2 == h->ws2 && x.images != plan.gen_buf) ++specific;
+        if (specific < EncoderPlan::kMaxSpecific) {
+            if (int rc = capture(images, feat, skip, normx, &e)) return rc;
+        } else {
+            // generic graph on the staging buffers: [image | feat | skip | normx]
+            const size_t n_img = (size_t)B * CHORE_IN_CH * H * W, n_feat = (size_t)B * (H / 4) * (W / 4) * 256,
+                         n_skip = (size_t)B * (H / 2) * (W / 2) * 64, n_nx = (size_t)B * (H / 4) * (W / 4) * 128;
+            const size_t need = n_img + n_feat + n_skip + n_nx;
+            if (plan.gen_floats < need) {
+                for (size_t i = 0; i < plan.entries.size();)      // graphs on the old staging buffer are stale
+                    if (plan.entries[i].images == plan.gen_buf && plan.gen_buf != nullptr) { cudaGraphExecDestroy(plan.entries[i].exec); plan.entries.erase(plan.entries.begin() + i); }
+                    else ++i;
+                if (plan.gen_buf) CHORE_CUDA(cudaFree(plan.gen_buf));
+                plan.gen_buf = nullptr; plan.gen_floats = 0;
+                CHORE_CUDA(cudaMalloc(&plan.gen_buf, need * sizeof(float)));
+                plan.gen_floats = need;
+            }
+            float *g_img = plan.gen_buf, *g_feat = g_img + n_img, *g_skip = g_feat + n_feat, *g_nx = g_skip + n_skip;
+            e = find(g_img, g_feat, g_skip, g_nx);
+            if (e == nullptr)
+                if (int rc = capture(g_img, g_feat, g_skip, g_nx, &e)) return rc;
+            CHORE_CUDA(cudaMemcpyAsync(g_img, images, n_img * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            CHORE_CUDA(cudaGraphLaunch(e->exec, st));
+            g_launch_count.fetch_add(e->kernels, std::memory_order_relaxed);
+            CHORE_CUDA(cudaMemcpyAsync(feat, g_feat, n_feat * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            CHORE_CUDA(cudaMemcpyAsync(skip, g_skip, n_skip * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            if (normx) CHORE_CUDA(cudaMemcpyAsync(normx, g_nx, n_nx * sizeof(float), cudaMemcpyDeviceToDevice, st));
             return CHORE_OK;
         }
-    if (!plan.cap_stream) CHORE_CUDA(cudaStreamCreateWithFlags(&plan.cap_stream, cudaStreamNonBlocking));
-    const uint64_t before = g_launch_count.load();
-    CHORE_CUDA(cudaStreamBeginCapture(plan.cap_stream, cudaStreamCaptureModeThreadLocal));
-    const int rc = record(plan.cap_stream);
-    cudaGraph_t graph = nullptr;
-    const cudaError_t ce = cudaStreamEndCapture(plan.cap_stream, &graph);
-    const uint64_t kernels = g_launch_count.load() - before;
-    g_launch_count.fetch_sub(kernels, std::memory_order_relaxed);   // recorded, not executed
-    if (rc != CHORE_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
-    if (ce != cudaSuccess) {
-        chore_set_error("encoder graph capture failed: %s", cudaGetErrorString(ce));
-        return CHORE_ERR_CUDA;
     }
-    cudaGraphExec_t exec = nullptr;
-    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (ie != cudaSuccess) {
-        chore_set_error("encoder graph instantiation failed: %s", cudaGetErrorString(ie));
-        return CHORE_ERR_CUDA;
-    }
-    if (plan.entries.size() >= 16) { cudaGraphExecDestroy(plan.entries.front().exec); plan.entries.erase(plan.entries.begin()); }
-    plan.entries.push_back({images, feat, skip, normx, h->ws, h->ws2, B, H, W, exec, kernels});
-    CHORE_CUDA(cudaGraphLaunch(exec, st));
-    g_launch_count.fetch_add(kernels, std::memory_order_relaxed);
+    CHORE_CUDA(cudaGraphLaunch(e->exec, st));
+    g_launch_count.fetch_add(e->kernels, std::memory_order_relaxed);
     return CHORE_OK;
 }
