@@ -126,6 +126,10 @@ __device__ __forceinline__ void cubic_coeffs_hx(float t, float (&c)[4]) {
     c[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
 }
 
+// One thread = one channel quad of a 2 x 2 block of outputs.  The four outputs read 4 x 4 taps each out of a shared 5 x 5
+// window of the low-resolution map (scale (I - 1) / (O - 1) < 1/2: neighbouring outputs move by at most one input pixel), so
+// the window is streamed row by row -- 25 loads instead of 64 -- and every output accumulates its taps in exactly the order
+// of the one-output-per-thread formulation (rows top to bottom, columns left to right, fmaf chains from 0): same bits.
 __global__ void __launch_bounds__(256) upadd_stats_kernel(const float *__restrict__ low, float *__restrict__ up, int IH, int IW, int C,
                                                           double *__restrict__ st_out) {
     chore_pdl_launch_dependents();
@@ -134,40 +138,77 @@ __global__ void __launch_bounds__(256) upadd_stats_kernel(const float *__restric
     const int b = blockIdx.y, tid = threadIdx.x, c4n = C / 4, cpg = C / kGroups, OW = IW * 2, OH = IH * 2;
     if (tid < kGroups * 2) acc[tid] = 0.f;
     __syncthreads();
-    const size_t n4 = (size_t)OH * OW * c4n;
+    const size_t nblk = (size_t)IH * IW * c4n;             // 2 x 2 output blocks x channel quads
     const int c4 = (int)((blockIdx.x * 256 + tid) % c4n);
     const float sy = OH > 1 ? (float)(IH - 1) / (float)(OH - 1) : 0.f;
     const float sx = OW > 1 ? (float)(IW - 1) / (float)(OW - 1) : 0.f;
     EwStats st;
     const float4 *lb = reinterpret_cast<const float4 *>(low) + (size_t)b * IH * IW * c4n + c4;
-    float4 *ub = reinterpret_cast<float4 *>(up) + (size_t)b * n4;
-    for (size_t i = (size_t)blockIdx.x * 256 + tid; i < n4; i += (size_t)gridDim.x * 256) {
+    float4 *ub = reinterpret_cast<float4 *>(up) + (size_t)b * OH * OW * c4n + c4;
+    for (size_t i = (size_t)blockIdx.x * 256 + tid; i < nblk; i += (size_t)gridDim.x * 256) {
         const size_t t = i / c4n;
-        const int ox = (int)(t % OW), oy = (int)(t / OW);
-        const float ry = sy * oy, rx = sx * ox;
-        const int iy = (int)floorf(ry), ix = (int)floorf(rx);
-        float cy[4], cx[4];
-        cubic_coeffs_hx(ry - iy, cy);
-        cubic_coeffs_hx(rx - ix, cx);
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int ox = 2 * (int)(t % IW), oy = 2 * (int)(t / IW);
+        int iy[2], ix[2];
+        float cy[2][4], cx[2][4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int yy = min(max(iy - 1 + j, 0), IH - 1);
-            float4 rsum = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int xx = min(max(ix - 1 + k, 0), IW - 1);
-                const float4 v = __ldg(lb + ((size_t)yy * IW + xx) * c4n);   // taps are shared by neighbouring outputs: keep them in L1
-                rsum.x = fmaf(v.x, cx[k], rsum.x); rsum.y = fmaf(v.y, cx[k], rsum.y);
-                rsum.z = fmaf(v.z, cx[k], rsum.z); rsum.w = fmaf(v.w, cx[k], rsum.w);
-            }
-            o.x = fmaf(rsum.x, cy[j], o.x); o.y = fmaf(rsum.y, cy[j], o.y);
-            o.z = fmaf(rsum.z, cy[j], o.z); o.w = fmaf(rsum.w, cy[j], o.w);
+        for (int r = 0; r < 2; ++r) {
+            const float ry = sy * (oy + r), rx = sx * (ox + r);
+            iy[r] = (int)floorf(ry); ix[r] = (int)floorf(rx);
+            cubic_coeffs_hx(ry - iy[r], cy[r]);
+            cubic_coeffs_hx(rx - ix[r], cx[r]);
         }
-        float4 u = __ldcg(ub + i);
-        u.x += o.x; u.y += o.y; u.z += o.z; u.w += o.w;
-        ub[i] = u;
-        st.add(u, cpg);
+        const bool dy = iy[1] != iy[0], dx = ix[1] != ix[0];          // the second output row / column starts one input pixel later
+        float4 o[2][2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) o[r][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {                                  // window row iy[0] - 1 + k
+            if (k == 4 && !dy) break;                                  // nobody reads the fifth row
+            const int yy = min(max(iy[0] - 1 + k, 0), IH - 1);
+            float4 v[5];
+#pragma unroll
+            for (int m = 0; m < 5; ++m) {
+                const int xx = min(max(ix[0] - 1 + m, 0), IW - 1);
+                v[m] = (m < 4 || dx) ? __ldg(lb + ((size_t)yy * IW + xx) * c4n) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            float4 rs[2];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const bool sh = c == 1 && dx;
+                float4 rsum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    const float4 a = sh ? v[m + 1] : v[m];
+                    rsum.x = fmaf(a.x, cx[c][m], rsum.x); rsum.y = fmaf(a.y, cx[c][m], rsum.y);
+                    rsum.z = fmaf(a.z, cx[c][m], rsum.z); rsum.w = fmaf(a.w, cx[c][m], rsum.w);
+                }
+                rs[c] = rsum;
+            }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const bool sh = r == 1 && dy;
+                // tap index of this window row for output row r: k (not shifted, k <= 3) or k - 1 (shifted, k >= 1)
+                if (sh ? k == 0 : k == 4) continue;
+                const float w = sh ? cy[r][k > 0 ? k - 1 : 0] : cy[r][k < 4 ? k : 3];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    o[r][c].x = fmaf(rs[c].x, w, o[r][c].x); o[r][c].y = fmaf(rs[c].y, w, o[r][c].y);
+                    o[r][c].z = fmaf(rs[c].z, w, o[r][c].z); o[r][c].w = fmaf(rs[c].w, w, o[r][c].w);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                float4 *dst = ub + ((size_t)(oy + r) * OW + (ox + c)) * c4n;
+                float4 u = __ldcg(dst);
+                u.x += o[r][c].x; u.y += o[r][c].y; u.z += o[r][c].z; u.w += o[r][c].w;
+                *dst = u;
+                st.add(u, cpg);
+            }
     }
     if (st_out) st.flush(acc, c4 * 4, cpg, st_out, b);
 }
@@ -454,7 +495,7 @@ ActH hourglass(CtxH &c, const std::string &p, int level, const ActH &x) {
     ActH low3 = conv_block(c, p + ".b3_" + L, low2, x.C, false);
     up1.st = c.slot();
     if (fork && !c.dry && c.rc == 0 && cudaStreamWaitEvent(c.st, ev_join, 0) != cudaSuccess) c.rc = CHORE_ERR_CUDA;
-    const size_t n4 = (size_t)up1.H * up1.W * up1.C / 4;
+    const size_t n4 = (size_t)low3.H * low3.W * low3.C / 4;          // one thread per 2 x 2 output block and channel quad
     HX_LAUNCH(c, upadd_stats_kernel, dim3(ew_grid(c, n4), c.B), 256, 0, low3.p, up1.p, low3.H, low3.W, low3.C, up1.st);
     c.top = mark;
     return up1;

@@ -156,3 +156,21 @@ def test_encoder_matches_round1_encoder_across_shapes(tmp_path):
     for k in _ENC_SHAPES:
         for name, a, b in zip(("feat", "skip", "normx"), outs["hx"][k], outs["tc1"][k]):
             assert rel_err(a, b) < 5e-5, (k, name, rel_err(a, b))
+
+
+def test_encode_with_ever_new_buffers_uses_the_generic_graph_and_agrees(net):
+    """chore_encode caches address-specific CUDA graphs; after four per shape it falls back to one generic graph on staging
+    buffers + copies.  Ten encodes of the same image into buffers that are all kept alive (ten distinct address sets) must agree."""
+    img0 = O.synth_images(4, B=1, size=256)
+    keep, first = [], None
+    for i in range(10):
+        img = img0.to(DEV).clone()
+        out = net.handle.encode(img)
+        torch.cuda.synchronize()
+        keep.append((img, out))
+        if first is None:
+            first = [o.clone() for o in out]
+        else:
+            for name, a, b in zip(("feat", "skip", "normx"), out, first):
+                assert rel_err(a, b) < 5e-5, (i, name, rel_err(a, b))
+    assert len({k[1][0].data_ptr() for k in keep}) == 10
