@@ -152,6 +152,7 @@ __device__ __forceinline__ void blend_vertex(const LbsParams &p, int b, int v, c
                                              int lane, float vp[3], float nk[3]) {
     float acc[3] = {0.f, 0.f, 0.f};
     const float *prow = p.posedirs + (size_t)v * 3 * p.P;
+#pragma unroll 4
     for (int k = lane; k < p.P; k += 32) {
         const float m = pm_s[k];
         acc[0] = fmaf(__ldg(prow + k), m, acc[0]);
@@ -231,16 +232,38 @@ __global__ void __launch_bounds__(256) lbs_vertex_bwd_kernel(const LbsParams p) 
     float gt[3] = {0.f, 0.f, 0.f};
     for (int v = v0 + warp; v < min(p.V, v0 + kVertsPerCta); v += 8) {
         float vp[3], nk[3], T[12];
-        blend_vertex(p, b, v, pm_s, beta_s, lane, vp, nk);
         blend_transform(p, v, A_s, lane, T);
         const float *gv = p.g_verts + ((size_t)b * p.V + v) * 3;
         const float g[3] = {__ldg(gv), __ldg(gv + 1), __ldg(gv + 2)};
         gt[0] += g[0]; gt[1] += g[1]; gt[2] += g[2];
-        // g_vposed = T.R^T g
+        // g_vposed = T.R^T g (does not depend on the vertex position: known before the pose blend shapes are read)
         float gvp[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) gvp[c] = T[c] * g[0] + T[4 + c] * g[1] + T[8 + c] * g[2];
         if (p.g_offsets && lane < 3) p.g_offsets[((size_t)b * p.V + v) * 3 + lane] = gvp[lane];
+        // ONE pass over the 3 x P pose blend shapes of the vertex (5.5 KB, L2 resident): the forward recompute
+        // v_posed += P[v][c][k] posemap[k] and the adjoint g_posemap[k] += sum_c P[v][c][k] gvp[c] share every load
+        {
+            float acc[3] = {0.f, 0.f, 0.f};
+            const float *prow = p.posedirs + (size_t)v * 3 * p.P;
+#pragma unroll 4
+            for (int k = lane; k < p.P; k += 32) {
+                const float p0 = __ldg(prow + k), p1 = __ldg(prow + p.P + k), p2 = __ldg(prow + 2 * p.P + k);
+                const float m = pm_s[k];
+                acc[0] = fmaf(p0, m, acc[0]); acc[1] = fmaf(p1, m, acc[1]); acc[2] = fmaf(p2, m, acc[2]);
+                atomicAdd(&gpm_s[k], p0 * gvp[0] + p1 * gvp[1] + p2 * gvp[2]);
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {                 // same operation order as blend_vertex
+                acc[c] = warp_sum(acc[c]);
+                float sb = 0.f;
+                const float *srow = p.shapedirs + ((size_t)v * 3 + c) * p.nb;
+                for (int k = 0; k < p.nb; ++k) sb = fmaf(__ldg(srow + k), beta_s[k], sb);
+                const float vs = __ldg(p.v_template + (size_t)v * 3 + c) + sb;
+                nk[c] = vs + acc[c];
+                vp[c] = nk[c] + (p.offsets ? __ldg(p.offsets + ((size_t)b * p.V + v) * 3 + c) : 0.f);
+            }
+        }
         // gA_j += w_vj * g (x) [vp;1]
         for (int j = lane; j < p.J; j += 32) {
             const float w = __ldg(p.weights + (size_t)v * p.J + j);
@@ -253,12 +276,6 @@ __global__ void __launch_bounds__(256) lbs_vertex_bwd_kernel(const LbsParams p) 
                     atomicAdd(&gA_s[j * 12 + r * 4 + 3], w * g[r]);
                 }
             }
-        }
-        // g_posemap[k] += sum_c P[v][c][k] gvp[c]
-        const float *prow = p.posedirs + (size_t)v * 3 * p.P;
-        for (int k = lane; k < p.P; k += 32) {
-            const float s = __ldg(prow + k) * gvp[0] + __ldg(prow + p.P + k) * gvp[1] + __ldg(prow + 2 * p.P + k) * gvp[2];
-            atomicAdd(&gpm_s[k], s);
         }
         // g_betas[k] += sum_c S[v][c][k] gvp[c]
         if (lane < p.nb) {
