@@ -80,6 +80,15 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.rows, self.proc, self.index = [], None, index
+        self.t0 = self.t1 = None
+
+    def mark(self, start: bool):
+        """Brackets the timed region; the sampler itself is started before the warm-up (nvidia-smi needs ~0.2-1 s to deliver its
+        first line -- longer on an 8-GPU box -- while 5 timed steps take 0.17 s)."""
+        if start:
+            self.t0 = time.perf_counter()
+        else:
+            self.t1 = time.perf_counter()
 
     def __enter__(self):
         try:
@@ -94,7 +103,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
     def __exit__(self, *a):
         if self.proc:
@@ -105,14 +114,20 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        if not sm:
+        ok = [(t, r) for t, r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        # samples inside the timed region (one sampling period of slack); otherwise everything seen under load (the sampler
+        # runs from the warm-up steps on, and the warm-up is the same workload)
+        inside = [r for t, r in ok if self.t0 is not None and self.t1 is not None and self.t0 - 0.1 <= t <= self.t1 + 0.1]
+        window = "timed region" if inside else "warm-up + timed region"
+        rows = inside or [r for _, r in ok]
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        sm = [float(r[0]) for r in rows]
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in rows)]
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 # =====================================================================================================
@@ -427,12 +442,14 @@ def run_ours(args, rank, world, local_rank):
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return t.item()
 
-    for _ in range(max(3, args.warmup)):
-        step_device(False)
-    barrier()
-    launches0 = chore_b200.launch_count()
     with ClockSampler(local_rank) as clk:
+        for _ in range(max(3, args.warmup)):
+            step_device(False)
+        barrier()
+        launches0 = chore_b200.launch_count()
+        clk.mark(True)
         ms_steps = timed(step_device, args.steps, record=True)
+        clk.mark(False)
     launches = chore_b200.launch_count() - launches0
     barrier()
     # per-image summary gathered over NCCL (the only collective on the path)
