@@ -662,10 +662,16 @@ __global__ void __launch_bounds__(kThreads, 1) query_bwd_tc_kernel(const TcParam
                     float a[32];
                     uint32_t m = 0;
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const float z = __uint_as_float(v[c]) + __ldg(bias + part * 32 + c);
-                        m |= (z > 0.f ? 1u : 0u) << c;
-                        a[c] = fmaxf(z, 0.f);
+                    for (int c4 = 0; c4 < 8; ++c4) {
+                        const float4 bb = __ldg(reinterpret_cast<const float4 *>(bias + part * 32) + c4);
+                        const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int c = c4 * 4 + j;
+                            const float z = __uint_as_float(v[c]) + bv[j];
+                            m |= (z > 0.f ? 1u : 0u) << c;
+                            a[c] = fmaxf(z, 0.f);
+                        }
                     }
                     mask[layer][part] = m;
                     if (layer < 2) {

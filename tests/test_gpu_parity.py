@@ -15,6 +15,7 @@ from oracle import chore_oracle as O
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
+CHAINED_TOL = 5e-2          # chained parameter gradients (see the module docstring); measured values go to the parity report
 ENC_TOL = 1e-4      # encoder output after ~60 GroupNorm + conv layers: measured 1.1e-5 .. 3.4e-5 (gpurun_out/parity_report.jsonl)
 E2E_TOL = 1e-4      # encoder + query end to end: measured <= 3.2e-5
 DEV = "cuda:0"
@@ -506,8 +507,10 @@ def test_smpl_fit_step_vs_oracle(net, sd, smpl_layer):
     assert rel_err(lc["df_h"], lo["df_h"]) < TOL, (lc["df_h"].item(), lo["df_h"].item())
     assert rel_err(lc["part"], lo["part"]) < TOL, (lc["part"].item(), lo["part"].item())
     assert rel_err(tot_c, tot_o) < TOL
-    for got, want in ((w.trans.grad, t.grad), (w.betas.grad, b.grad), (w.pose.grad, p.grad)):
-        assert rel_err(got, want) < 1e-1
+    chained = {n: rel_err(got, want) for n, got, want in (("trans", w.trans.grad, t.grad), ("betas", w.betas.grad, b.grad), ("pose", w.pose.grad, p.grad))}
+    report("smpl_fit_step_chained_gradients_vs_oracle", **chained)
+    for n, e in chained.items():
+        assert e < CHAINED_TOL, (n, e)
     # stage 1: identical vertices -> per-vertex gradient of the field losses
     v_c = verts.detach().contiguous().to(DEV).requires_grad_(True)
     net.query(v_c, crop_center=cc.to(DEV))
@@ -876,8 +879,10 @@ def test_fit_smpl_full_step_vs_golden(net, smpl_layer):
     assert rel_err(total, g["total"]) < TOL
     total.backward()
     # chained gradients: sums of thousands of per-vertex terms with ReLU / clamp gates (see the module docstring)
-    for name in ("trans", "global_pose", "body_pose", "hand_pose", "top_betas", "other_betas"):
-        assert rel_err(getattr(split, name).grad, g[f"grad_{name}"]) < 5e-2, (name, rel_err(getattr(split, name).grad, g[f"grad_{name}"]))
+    chained = {name: rel_err(getattr(split, name).grad, g[f"grad_{name}"]) for name in ("trans", "global_pose", "body_pose", "hand_pose", "top_betas", "other_betas")}
+    report("fit_smpl_full_chained_gradients_vs_reference", **chained)
+    for name, e in chained.items():
+        assert e < CHAINED_TOL, (name, e)
     # the fused (autograd-free) step computes the same loss and the same gradients as the autograd path
     split2 = fit.split_smpl(w)
     R, t, s = torch.eye(3, device=DEV).repeat(2, 1, 1), torch.zeros(2, 3, device=DEV), torch.ones(2, device=DEV)
