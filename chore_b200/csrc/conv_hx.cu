@@ -12,9 +12,11 @@
 //     epilogue, so no separate statistics pass over the tensor is needed;
 //   * is persistent over work items (pixel tile x output-channel slice x K slice).  A tcgen05.mma with both operands in
 //     shared memory costs >= 64 cycles for any N <= 128 (the 4 KB A operand is re-read per instruction), so the
-//     low-resolution levels, which have fewer tiles than SMs, split the K loop (taps x 64-channel blocks) over CTAs:
-//     the non-leading parts park their fp32 partial tile in an L2-resident scratch and bump a per-tile counter, the
-//     leading part adds them in its epilogue (fixed order: deterministic).
+//     low-resolution levels, which have fewer tiles than SMs, split the K loop (taps x 64-channel blocks) over the CTAs of
+//     a thread-block cluster (rank = K part).  32-column chunk c of the tile is finished by part c mod k: the other parts
+//     push their fp32 partial chunk into the owner's shared memory (st.async + mbarrier complete_tx; the owner's halo
+//     buffers and weight ring are idle once its own MMAs are done, which it announces with a remote mbarrier arrive) and
+//     the owner adds the partials in sender order (deterministic).
 // Replaces the F.group_norm + ReLU + F.conv2d triples of ConvBlock.forward (model/net_util.py:374-396) and the 1x1
 // convolutions of HGFilter.forward (model/HGFilters.py:173-183).
 #include "common.cuh"
