@@ -10,7 +10,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libchore_b200.so")
-SOURCES = ["runtime.cu", "query.cu", "query_tc.cu", "query_tc2.cu", "query_g.cu", "conv_tc.cu", "conv_hx.cu", "encoder.cu", "encoder_hx.cu", "lbs.cu", "fit_loss.cu", "generator.cu", "contact.cu", "silhouette.cu"]
+SOURCES = ["runtime.cu", "query.cu", "query_tc.cu", "query_bwd_tc.cu", "query_tc2.cu", "query_g.cu", "conv_tc.cu", "conv_hx.cu", "encoder.cu", "encoder_hx.cu", "lbs.cu", "fit_loss.cu", "generator.cu", "contact.cu", "silhouette.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "--expt-relaxed-constexpr",
               "-Xptxas", "-v"]

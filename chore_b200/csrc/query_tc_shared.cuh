@@ -22,6 +22,8 @@ constexpr size_t kStreamBytes = (size_t)kBigUnits * kPanelBytes + 4 * (size_t)kS
 constexpr int kThreads = 14 * 32;
 constexpr int kGatherWarp0 = 2, kEpiWarp0 = 6;
 constexpr size_t kSmemBytes = 1024 + (size_t)kNA * kStageA + (size_t)kNACT * kStageA + (size_t)kNW * kPanelBytes + 512;
+constexpr int kBwdUnits = 12 + 4 + 4 + 4 + 4 + 12;     // backward weight stream per head: F1, F2, F3, B3, B2, B1 panels of 16 KB
+constexpr int kGXLd = 384;                             // leading dimension of the gX scratch (query_bwd_tc.cu)
 
 constexpr float kFx = static_cast<float>(979.7844 / 2048. * 2048);
 constexpr float kFy = static_cast<float>(979.840 / 2048. * 2048);
